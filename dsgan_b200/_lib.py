@@ -1,0 +1,101 @@
+"""ctypes binding of the C ABI declared in include/dsgan_b200.h.
+
+Prototypes are parsed from the header itself, so the Python side cannot drift from the ABI.  There is no
+fallback of any kind: a missing library or a non-sm_100 device raises.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(HERE), "include", "dsgan_b200.h")
+LIB_PATH = os.path.join(HERE, "libdsgan_b200.so")
+
+
+class ConvDesc(ctypes.Structure):
+    """Mirror of dsgan_conv_desc."""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("dtype", "N", "Hi", "Wi", "Ci", "Ho", "Wo", "Co", "kh", "kw", "stride", "pad", "transposed",
+                 "ld_in", "ld_out", "ld_aux", "ld_pre")] + \
+               [(n, ctypes.c_longlong) for n in ("w_sco", "w_sci", "w_sky", "w_skx")] + \
+               [(n, ctypes.c_int) for n in ("act", "dact", "accumulate")]
+
+
+_SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
+            "unsigned long long": ctypes.c_ulonglong, "size_t": ctypes.c_size_t, "unsigned": ctypes.c_uint}
+
+
+def parse_header(path=HEADER):
+    """-> {name: (restype, [argtypes])} for every `dsgan_*` prototype in the header."""
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", " ", src)
+    protos = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(dsgan_\w+)\s*\(([^;{}]*?)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if "typedef" in ret or "struct" in ret:
+            continue
+        restype = ctypes.c_char_p if "char" in ret else _SCALARS.get(ret.replace("const ", "").strip(), ctypes.c_int)
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    ty = " ".join(a.replace("const ", "").split()[:-1])
+                    argtypes.append(_SCALARS[ty])
+        protos[name] = (restype, argtypes)
+    return protos
+
+
+class DsganError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise DsganError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(dsgan_b200 has no CPU or library fallback)" % LIB_PATH)
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.protos = parse_header()
+        for name, (restype, argtypes) in self.protos.items():
+            fn = getattr(self.cdll, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype, fn.argtypes = restype, argtypes
+        if self.cdll.dsgan_abi_version() != 1:
+            raise DsganError("ABI version mismatch")
+
+    def last_error(self):
+        return self.cdll.dsgan_last_error().decode()
+
+    def __getattr__(self, short):
+        """lib.conv_fwd(...) -> dsgan_conv_fwd(...) with error checking."""
+        fn = getattr(self.cdll, "dsgan_" + short)
+        if fn.restype is not ctypes.c_int:
+            return fn
+
+        def call(*args):
+            if fn(*args) != 0:
+                raise DsganError("dsgan_%s: %s" % (short, self.last_error()))
+        call.__name__ = short
+        setattr(self, short, call)
+        return call
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib
+
+
+def require_device():
+    """Fail loudly unless a B200 is the current device."""
+    import torch
+    if not torch.cuda.is_available():
+        raise DsganError("dsgan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    lib().device_check()

@@ -1,0 +1,88 @@
+// Shared helpers for the dsgan_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+namespace dsgan {
+
+typedef __nv_bfloat16 bf16;
+
+enum { DT_F32 = 0, DT_BF16 = 1 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_GELU = 3, ACT_SIGMOID = 4 };
+
+// ---- error / bookkeeping (host) -------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+extern unsigned long long g_launches;
+#define DS_LAUNCHED(name) (++::dsgan::g_launches, ::dsgan::check_launch(name))
+#define DS_REQUIRE(cond, ...) do { if (!(cond)) { ::dsgan::set_error(__VA_ARGS__); return 1; } } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- element access -------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- activations ----------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float act_fwd(int act, float v) {
+  switch (act) {
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    case ACT_LEAKY: return v > 0.f ? v : 0.2f * v;
+    case ACT_GELU: return gelu_f(v);
+    case ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
+    default: return v;
+  }
+}
+// derivative; `a` is the activation OUTPUT for relu/leaky/sigmoid and the PRE-activation for gelu
+__device__ __forceinline__ float act_bwd(int act, float a) {
+  switch (act) {
+    case ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case ACT_LEAKY: return a > 0.f ? 1.f : 0.2f;
+    case ACT_GELU: return gelu_grad_f(a);
+    case ACT_SIGMOID: return a * (1.f - a);
+    default: return 1.f;
+  }
+}
+
+// ---- reductions -----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; every thread gets the result. `sh` must hold >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sh[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+}  // namespace dsgan
+
+#define DS_DISPATCH_DT(dt, ...)                                     \
+  do {                                                              \
+    if ((dt) == ::dsgan::DT_F32) { typedef float T; __VA_ARGS__; }  \
+    else if ((dt) == ::dsgan::DT_BF16) { typedef ::dsgan::bf16 T; __VA_ARGS__; } \
+    else { ::dsgan::set_error("bad dtype %d", (int)(dt)); return 1; } \
+  } while (0)

@@ -1,0 +1,160 @@
+// Layout conversion and small elementwise kernels (HBM-bound; coalesced on the NHWC channel axis).
+#include "common.cuh"
+#include "../../include/dsgan_b200.h"
+using namespace dsgan;
+
+// ---- NCHW fp32 <-> NHWC T --------------------------------------------------------------------
+template <typename T>
+__global__ void k_nchw_to_nhwc(const float* __restrict__ src, T* __restrict__ dst, int C, long long HW, int ld,
+                               float scale, float shift, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over n*HW pixels
+  if (i >= total) return;
+  long long n = i / HW, p = i - n * HW;
+  const float* s = src + n * C * HW + p;
+  T* d = dst + i * ld;
+  for (int c = 0; c < C; ++c) stf(d + c, s[(long long)c * HW] * scale + shift);
+}
+template <typename T>
+__global__ void k_nhwc_to_nchw(const T* __restrict__ src, int ld, float* __restrict__ dst, int C, long long HW,
+                               float alpha, int acc, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long n = i / HW, p = i - n * HW;
+  const T* s = src + i * ld;
+  float* d = dst + n * C * HW + p;
+  for (int c = 0; c < C; ++c) {
+    float v = alpha * ldf(s + c);
+    if (acc) v += d[(long long)c * HW];
+    d[(long long)c * HW] = v;
+  }
+}
+template <typename T>
+__global__ void k_copy_channels(const T* __restrict__ src, int lds, T* __restrict__ dst, int ldd, long long npix,
+                                int C, int acc) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = npix * C;
+  for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long p = i / C;
+    int c = (int)(i - p * C);
+    float v = ldf(src + p * lds + c);
+    if (acc) v += ldf(dst + p * ldd + c);
+    stf(dst + p * ldd + c, v);
+  }
+}
+template <typename T>
+__global__ void k_add_n(T* __restrict__ out, long long n, const T* a, const T* b, const T* c, const T* d,
+                        const T* e) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = ldf(a + i) + ldf(b + i);
+    if (c) v += ldf(c + i);
+    if (d) v += ldf(d + i);
+    if (e) v += ldf(e + i);
+    stf(out + i, v);
+  }
+}
+template <typename T>
+__global__ void k_scale_nc_fwd(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ y,
+                               long long HW, int C, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long n = i / ((long long)HW * C);
+    stf(y + i, ldf(x + i) * s[n * C + c]);
+  }
+}
+// grid: (pixel chunks, N); block: 256 threads = (C-lane, pixel-lane)
+template <typename T>
+__global__ void k_scale_nc_bwd_reduce(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ ds,
+                                      long long HW, int C, int chunk) {
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * chunk;
+  const long long p1 = min(p0 + (long long)chunk, HW);
+  const int cl = min(C, (int)blockDim.x);
+  const int pl = blockDim.x / cl;
+  const int tc = threadIdx.x % cl, tp = threadIdx.x / cl;
+  if (tp >= pl) return;
+  for (int c = tc; c < C; c += cl) {
+    float acc = 0.f;
+    for (long long p = p0 + tp; p < p1; p += pl) {
+      long long o = ((long long)n * HW + p) * C + c;
+      acc += ldf(x + o) * ldf(dy + o);
+    }
+    atomicAdd(ds + (long long)n * C + c, acc);
+  }
+}
+template <typename T>
+__global__ void k_scale_nc_bwd_apply(const T* __restrict__ dy, const float* __restrict__ s,
+                                     const float* __restrict__ davg, const float* __restrict__ dmax,
+                                     const int* __restrict__ amax, T* __restrict__ dx, long long HW, int C, int acc,
+                                     long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float inv = 1.0f / (float)HW;
+  for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long np = i / C;
+    long long n = np / HW;
+    int p = (int)(np - n * HW);
+    long long nc = n * C + c;
+    float v = ldf(dy + i) * s[nc] + davg[nc] * inv + (amax[nc] == p ? dmax[nc] : 0.f);
+    if (acc) v += ldf(dx + i);
+    stf(dx + i, v);
+  }
+}
+
+static inline int grid_for(long long n, int block, int cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" {
+int dsgan_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int C, int H, int W, int ld_dst, float scale,
+                       float shift, void* stream) {
+  long long HW = (long long)H * W, total = HW * N;
+  DS_DISPATCH_DT(dtype, (k_nchw_to_nhwc<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            src, (T*)dst, C, HW, ld_dst, scale, shift, total)));
+  return DS_LAUNCHED("nchw_to_nhwc");
+}
+int dsgan_nhwc_to_nchw(const void* src, int dtype, int ld_src, float* dst, int N, int C, int H, int W, float alpha,
+                       int accumulate, void* stream) {
+  long long HW = (long long)H * W, total = HW * N;
+  DS_DISPATCH_DT(dtype, (k_nhwc_to_nchw<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)src, ld_src, dst, C, HW, alpha, accumulate, total)));
+  return DS_LAUNCHED("nhwc_to_nchw");
+}
+int dsgan_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int dtype, long long npix, int C,
+                        int accumulate, void* stream) {
+  DS_DISPATCH_DT(dtype, (k_copy_channels<T><<<grid_for(npix * C, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)src, ld_src, (T*)dst, ld_dst, npix, C, accumulate)));
+  return DS_LAUNCHED("copy_channels");
+}
+int dsgan_add_n(void* out, int dtype, long long n, const void* a, const void* b, const void* c, const void* d,
+                const void* e, void* stream) {
+  DS_REQUIRE(a && b, "add_n needs at least two inputs");
+  DS_DISPATCH_DT(dtype, (k_add_n<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (T*)out, n, (const T*)a, (const T*)b, (const T*)c, (const T*)d, (const T*)e)));
+  return DS_LAUNCHED("add_n");
+}
+int dsgan_scale_nc_fwd(const void* x, const float* s, void* y, int dtype, int N, long long HW, int C, void* stream) {
+  long long total = (long long)N * HW * C;
+  DS_DISPATCH_DT(dtype, (k_scale_nc_fwd<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)x, s, (T*)y, HW, C, total)));
+  return DS_LAUNCHED("scale_nc_fwd");
+}
+int dsgan_scale_nc_bwd_reduce(const void* x, const void* dy, float* ds, int dtype, int N, long long HW, int C,
+                              void* stream) {
+  cudaMemsetAsync(ds, 0, sizeof(float) * N * C, (cudaStream_t)stream);
+  int chunk = 256;
+  dim3 grid(cdiv(HW, chunk), N);
+  DS_DISPATCH_DT(dtype, (k_scale_nc_bwd_reduce<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy,
+                                                                                         ds, HW, C, chunk)));
+  return DS_LAUNCHED("scale_nc_bwd_reduce");
+}
+int dsgan_scale_nc_bwd_apply(const void* dy, const float* s, const float* davg, const float* dmax, const int* argmax,
+                             void* dx, int dtype, int N, long long HW, int C, int accumulate, void* stream) {
+  long long total = (long long)N * HW * C;
+  DS_DISPATCH_DT(dtype, (k_scale_nc_bwd_apply<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)dy, s, davg, dmax, argmax, (T*)dx, HW, C, accumulate, total)));
+  return DS_LAUNCHED("scale_nc_bwd_apply");
+}
+}

@@ -1,0 +1,224 @@
+// MaxPool2d(k) forward/backward and the CA channel-attention gate (global avg+max pooling, shared
+// fc1->PReLU->fc2, sigmoid) forward/backward.  Reference: MixConvNeXtML.py:5-22,68-74,333-354; vgg.py pools.
+#include "common.cuh"
+#include "../../include/dsgan_b200.h"
+using namespace dsgan;
+
+namespace {
+template <typename T>
+__global__ void k_maxpool_fwd(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int H, int W, int C,
+                              int k, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int Ho = H / k, Wo = W / k;
+  const int c = (int)(i % C);
+  const long long op = i / C;
+  const int ox = (int)(op % Wo);
+  const long long r = op / Wo;
+  const int oy = (int)(r % Ho);
+  const long long n = r / Ho;
+  const T* xb = x + ((n * H + (long long)oy * k) * W + (long long)ox * k) * ldx + c;
+  float m = -INFINITY;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) m = fmaxf(m, ldf(xb + ((long long)ky * W + kx) * ldx));
+  stf(y + op * ldy + c, m);
+}
+
+template <typename T>
+__global__ void k_maxpool_bwd(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int lddy,
+                              T* __restrict__ dx, int lddx, int H, int W, int C, int k, int acc, int relu_mask,
+                              long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int Ho = H / k, Wo = W / k;
+  const int c = (int)(i % C);
+  const long long op = i / C;
+  const int ox = (int)(op % Wo);
+  const long long r = op / Wo;
+  const int oy = (int)(r % Ho);
+  const long long n = r / Ho;
+  const long long win = (n * H + (long long)oy * k) * W + (long long)ox * k;
+  const T* xb = x + win * ldx + c;
+  float m = -INFINITY;
+  int am = 0;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      const float v = ldf(xb + ((long long)ky * W + kx) * ldx);
+      if (v > m) { m = v; am = ky * k + kx; }  // strict: first maximum in scan order (Q5)
+    }
+  const float g = ldf(dy + op * lddy + c);
+  T* db = dx + win * lddx + c;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      T* o = db + ((long long)ky * W + kx) * lddx;
+      float v = (ky * k + kx == am) ? g : 0.f;
+      if (acc) v += ldf(o);
+      if (relu_mask && !(ldf(xb + ((long long)ky * W + kx) * ldx) > 0.f)) v = 0.f;
+      stf(o, v);
+    }
+}
+
+__device__ __forceinline__ unsigned long long pack_max(float v, unsigned p) {
+  unsigned u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - p);
+}
+__device__ __forceinline__ void unpack_max(unsigned long long k, float& v, int& p) {
+  unsigned u = (unsigned)(k >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  v = __uint_as_float(u);
+  p = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+}
+
+// grid (pixel chunks, N)
+template <typename T>
+__global__ void k_ca_pool(const T* __restrict__ x, long long HW, int C, float* __restrict__ sum,
+                          unsigned long long* __restrict__ packed, int chunk) {
+  const int cl = C < 64 ? C : 64, pl = blockDim.x / cl;
+  const int tc = threadIdx.x % cl, tp = threadIdx.x / cl;
+  if (tp >= pl) return;
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * chunk, p1 = min(p0 + (long long)chunk, HW);
+  for (int c = tc; c < C; c += cl) {
+    float s = 0.f, m = -INFINITY;
+    unsigned am = 0;
+    for (long long p = p0 + tp; p < p1; p += pl) {
+      const float v = ldf(x + ((long long)n * HW + p) * C + c);
+      s += v;
+      if (v > m) { m = v; am = (unsigned)p; }
+    }
+    if (p0 + tp < p1) {
+      atomicAdd(sum + (long long)n * C + c, s);
+      atomicMax(packed + (long long)n * C + c, pack_max(m, am));
+    }
+  }
+}
+
+// one block per sample.  smem: avg[C], mx[C], ha[Cr], hm[Cr]
+__global__ void k_ca_mlp(const unsigned long long* __restrict__ packed, long long HW,
+                         int C, const float* __restrict__ fc1, const float* __restrict__ slope,
+                         const float* __restrict__ fc2, float* avg /* in: plane sums, out: means */,
+                         float* __restrict__ mx,
+                         int* __restrict__ argmax, float* __restrict__ s) {
+  extern __shared__ float sm[];
+  const int Cr = C / 8, n = blockIdx.x;
+  float* a = sm; float* m = sm + C; float* ha = m + C; float* hm = ha + Cr;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mv; int mp;
+    unpack_max(packed[(long long)n * C + c], mv, mp);
+    const float av = avg[(long long)n * C + c] / (float)HW;
+    a[c] = av; m[c] = mv;
+    avg[(long long)n * C + c] = av; mx[(long long)n * C + c] = mv; argmax[(long long)n * C + c] = mp;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float sl = slope[0];
+  for (int j = w; j < Cr; j += nw) {
+    float pa = 0.f, pm = 0.f;
+    for (int c = lane; c < C; c += 32) { const float f = fc1[j * C + c]; pa = fmaf(f, a[c], pa); pm = fmaf(f, m[c], pm); }
+    pa = warp_sum(pa); pm = warp_sum(pm);
+    if (lane == 0) { ha[j] = pa; hm[j] = pm; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float z = 0.f;
+    for (int j = 0; j < Cr; ++j) {
+      const float pa = ha[j] > 0.f ? ha[j] : sl * ha[j], pm = hm[j] > 0.f ? hm[j] : sl * hm[j];
+      z = fmaf(fc2[c * Cr + j], pa + pm, z);
+    }
+    s[(long long)n * C + c] = 1.0f / (1.0f + __expf(-z));
+  }
+}
+
+__global__ void k_ca_bwd(const float* __restrict__ ds, const float* __restrict__ s, const float* __restrict__ avg,
+                         const float* __restrict__ mx, int C, const float* __restrict__ fc1,
+                         const float* __restrict__ slope, const float* __restrict__ fc2, float* __restrict__ dfc1,
+                         float* __restrict__ dslope, float* __restrict__ dfc2, float* __restrict__ davg,
+                         float* __restrict__ dmax) {
+  extern __shared__ float sm[];
+  const int Cr = C / 8, n = blockIdx.x;
+  float* a = sm; float* m = a + C; float* dz = m + C; float* ha = dz + C; float* hm = ha + Cr;
+  float* dha = hm + Cr; float* dhm = dha + Cr; float* red = dhm + Cr;  // red[32]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const long long o = (long long)n * C + c;
+    a[c] = avg[o]; m[c] = mx[o];
+    const float sv = s[o];
+    dz[c] = ds[o] * sv * (1.f - sv);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float sl = slope[0];
+  float dsl = 0.f;
+  for (int j = w; j < Cr; j += nw) {
+    float pa = 0.f, pm = 0.f, dp = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float f = fc1[j * C + c];
+      pa = fmaf(f, a[c], pa); pm = fmaf(f, m[c], pm);
+      dp = fmaf(fc2[c * Cr + j], dz[c], dp);
+    }
+    pa = warp_sum(pa); pm = warp_sum(pm); dp = warp_sum(dp);
+    if (lane == 0) {
+      ha[j] = pa; hm[j] = pm;
+      dha[j] = dp * (pa > 0.f ? 1.f : sl);
+      dhm[j] = dp * (pm > 0.f ? 1.f : sl);
+      dsl += dp * ((pa > 0.f ? 0.f : pa) + (pm > 0.f ? 0.f : pm));
+    }
+  }
+  dsl = block_sum(dsl, red);
+  if (threadIdx.x == 0) atomicAdd(dslope, dsl);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float da = 0.f, dm = 0.f;
+    for (int j = 0; j < Cr; ++j) {
+      const float pa = ha[j] > 0.f ? ha[j] : sl * ha[j], pm = hm[j] > 0.f ? hm[j] : sl * hm[j];
+      atomicAdd(dfc2 + c * Cr + j, dz[c] * (pa + pm));
+      atomicAdd(dfc1 + j * C + c, dha[j] * a[c] + dhm[j] * m[c]);
+      const float f = fc1[j * C + c];
+      da = fmaf(f, dha[j], da); dm = fmaf(f, dhm[j], dm);
+    }
+    davg[(long long)n * C + c] = da; dmax[(long long)n * C + c] = dm;
+  }
+}
+}  // namespace
+
+extern "C" {
+int dsgan_maxpool_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int N, int H, int W, int C, int k,
+                      void* stream) {
+  DS_REQUIRE(k >= 1 && H % k == 0 && W % k == 0, "maxpool: H,W (%d,%d) must be multiples of k=%d", H, W, k);
+  const long long total = (long long)N * (H / k) * (W / k) * C;
+  DS_DISPATCH_DT(dtype, (k_maxpool_fwd<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld_x, (T*)y,
+                                                                                             ld_y, H, W, C, k, total)));
+  return DS_LAUNCHED("maxpool_fwd");
+}
+int dsgan_maxpool_bwd(const void* x, int ld_x, const void* dy, int ld_dy, void* dx, int ld_dx, int dtype, int N, int H,
+                      int W, int C, int k, int accumulate, int relu_mask, void* stream) {
+  DS_REQUIRE(k >= 1 && H % k == 0 && W % k == 0, "maxpool: H,W (%d,%d) must be multiples of k=%d", H, W, k);
+  const long long total = (long long)N * (H / k) * (W / k) * C;
+  DS_DISPATCH_DT(dtype, (k_maxpool_bwd<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                            (const T*)x, ld_x, (const T*)dy, ld_dy, (T*)dx, ld_dx, H, W, C, k, accumulate, relu_mask,
+                            total)));
+  return DS_LAUNCHED("maxpool_bwd");
+}
+int dsgan_ca_fwd(const void* x, int dtype, int N, long long HW, int C, const float* fc1, const float* slope,
+                 const float* fc2, float* avg, float* mx, int* argmax, float* s, void* workspace, void* stream) {
+  DS_REQUIRE(C % 8 == 0 && C <= 2048, "ca_fwd: C=%d unsupported", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* packed = (unsigned long long*)workspace;
+  cudaMemsetAsync(avg, 0, sizeof(float) * N * C, st);
+  cudaMemsetAsync(packed, 0, sizeof(unsigned long long) * N * C, st);
+  const int chunk = 512;
+  dim3 grid(cdiv(HW, chunk), N);
+  DS_DISPATCH_DT(dtype, (k_ca_pool<T><<<grid, 256, 0, st>>>((const T*)x, HW, C, avg, packed, chunk)));
+  if (DS_LAUNCHED("ca_pool")) return 1;
+  const size_t smem = sizeof(float) * (2 * C + 2 * (C / 8));
+  k_ca_mlp<<<N, 256, smem, st>>>(packed, HW, C, fc1, slope, fc2, avg, mx, argmax, s);
+  return DS_LAUNCHED("ca_mlp");
+}
+int dsgan_ca_bwd(const float* ds, const float* s, const float* avg, const float* mx, int N, int C, const float* fc1,
+                 const float* slope, const float* fc2, float* dfc1, float* dslope, float* dfc2, float* davg,
+                 float* dmax, void* stream) {
+  const size_t smem = sizeof(float) * (3 * C + 4 * (C / 8) + 32);
+  k_ca_bwd<<<N, 256, smem, (cudaStream_t)stream>>>(ds, s, avg, mx, C, fc1, slope, fc2, dfc1, dslope, dfc2, davg, dmax);
+  return DS_LAUNCHED("ca_bwd");
+}
+}

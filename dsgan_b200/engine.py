@@ -1,0 +1,426 @@
+"""Host-side execution engine: NHWC device tensors, a reverse-mode tape, and thin wrappers that hand raw
+pointers to the C ABI (include/dsgan_b200.h).  PyTorch is used for device memory and streams only — no
+torch operator computes anything on the hot path.
+
+Gradient protocol: every backward kernel can either overwrite or accumulate (`accumulate` flag of the ABI).
+`Var.grad_out()` returns the gradient buffer plus that flag, so fan-out (a tensor consumed by several ops, e.g.
+the encoder skips R1..R4, MixConvNeXtML.py:476-491) costs no extra pass.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._lib import ConvDesc, lib, require_device
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+
+
+class Var:
+    """An NHWC activation (or a channel slice of one) that can carry a gradient."""
+    __slots__ = ("t", "ptr", "N", "H", "W", "C", "ld", "es", "g", "parent", "coff", "fused_act")
+
+    def __init__(self, t, N, H, W, C, ld=None, ptr=None, parent=None, coff=0):
+        self.t, self.N, self.H, self.W, self.C = t, N, H, W, C
+        self.ld = C if ld is None else ld
+        self.es = t.element_size()
+        self.ptr = t.data_ptr() if ptr is None else ptr
+        self.g = None          # dense gradient tensor [N,H,W,C] (same dtype as t)
+        self.parent, self.coff = parent, coff
+        self.fused_act = None  # (act, aux Var): this tensor is act(aux) and its grad is stored w.r.t. aux
+
+    @property
+    def npix(self):
+        return self.N * self.H * self.W
+
+    def slice(self, c0, c):
+        return Var(self.t, self.N, self.H, self.W, c, ld=self.ld, ptr=self.ptr + c0 * self.es, parent=self, coff=c0)
+
+    # -- gradient access -------------------------------------------------------------------
+    def grad_out(self):
+        """-> (ptr, ld, accumulate) of the buffer a backward kernel must write this Var's gradient into."""
+        if self.parent is not None:
+            par = self.parent
+            if par.parent is None and par.g is None:
+                # a slice is written before its whole parent: start the parent's gradient at zero so that
+                # sibling slices (and later whole-tensor writers) can all accumulate
+                par.g = torch.zeros((par.N, par.H, par.W, par.C), dtype=par.t.dtype, device=par.t.device)
+            p, ld, _acc = par.grad_out()
+            return p + self.coff * self.es, ld, 1
+        if self.g is None:
+            self.g = torch.empty((self.N, self.H, self.W, self.C), dtype=self.t.dtype, device=self.t.device)
+            return self.g.data_ptr(), self.C, 0
+        return self.g.data_ptr(), self.C, 1
+
+    def grad_in(self):
+        """-> (ptr, ld) of the accumulated gradient, or None if nothing flowed here."""
+        if self.parent is not None:
+            r = self.parent.grad_in()
+            return None if r is None else (r[0] + self.coff * self.es, r[1])
+        return None if self.g is None else (self.g.data_ptr(), self.C)
+
+
+class Param:
+    """fp32 master parameter + fp32 gradient, both views into per-network flat buffers."""
+    __slots__ = ("name", "data", "grad", "cache")
+
+    def __init__(self, name, data, grad):
+        self.name, self.data, self.grad, self.cache = name, data, grad, {}
+
+    @property
+    def ptr(self):
+        return self.data.data_ptr()
+
+    @property
+    def gptr(self):
+        return self.grad.data_ptr()
+
+
+class Ctx:
+    """One engine context per device: dtype mode, tape, scratch, kernel wrappers."""
+
+    def __init__(self, device="cuda:0", precision="bf16"):
+        require_device()
+        self.L = lib()
+        self.device = torch.device(device)
+        assert precision in ("bf16", "fp32")
+        self.precision = precision
+        self.dt = BF16 if precision == "bf16" else F32
+        self.tdtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.tape = []
+        self.param_grads = True   # False while D is frozen in the G step (pix2pix_model.py:214)
+        self.no_grad = False
+
+    # ---- memory ---------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def new(self, N, H, W, C):
+        return Var(torch.empty((N, H, W, C), dtype=self.tdtype, device=self.device), N, H, W, C)
+
+    def f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def zeros_f32(self, *shape):
+        t = self.f32(*shape)
+        self.L.memset(t.data_ptr(), 0, t.numel() * 4, self.stream)
+        return t
+
+    def zero_(self, t):
+        self.L.memset(t.data_ptr(), 0, t.numel() * t.element_size(), self.stream)
+
+    def record(self, fn):
+        if not self.no_grad:
+            self.tape.append(fn)
+
+    def backward(self, tape=None):
+        """Run (and drop) a tape in reverse; default: the context's current tape."""
+        if tape is None:
+            tape, self.tape = self.tape, []
+        while tape:  # popping lets each layer's activations and gradients be freed as soon as it is done
+            tape.pop()()
+
+    def take_tape(self):
+        """Detach the recorded tape (e.g. keep G's graph alive across the D step)."""
+        tape, self.tape = self.tape, []
+        return tape
+
+    def clear(self):
+        self.tape = []
+
+    # ---- raw kernel wrappers (pointer level) ---------------------------------------------------
+    def _desc(self, N, Hi, Wi, Ci, Ho, Wo, Co, k, stride, pad, transposed, ld_in, ld_out, wst, act=0, dact=0, acc=0,
+              ld_aux=0, ld_pre=0):
+        d = ConvDesc()
+        d.dtype = self.dt
+        d.N, d.Hi, d.Wi, d.Ci, d.Ho, d.Wo, d.Co = N, Hi, Wi, Ci, Ho, Wo, Co
+        d.kh = d.kw = k
+        d.stride, d.pad, d.transposed = stride, pad, int(transposed)
+        d.ld_in, d.ld_out, d.ld_aux, d.ld_pre = ld_in, ld_out, ld_aux, ld_pre
+        d.w_sco, d.w_sci, d.w_sky, d.w_skx = wst
+        d.act, d.dact, d.accumulate = act, dact, acc
+        return d
+
+    def conv_raw(self, geom, xin, w_ptr, wst, bias_ptr, out, act=0, dact=0, acc=0, aux=None, pre=None,
+                 transposed=False):
+        """geom = (N,Hi,Wi,Ci,Ho,Wo,Co,k,stride,pad); xin/out/aux/pre = (ptr, ld)."""
+        assert not (acc and dact and dact != ACT_RELU), "accumulate+dact is only exact for the idempotent ReLU mask"
+        N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+        d = self._desc(N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p, transposed, xin[1], out[1], wst, act, dact, acc,
+                       aux[1] if aux else 0, pre[1] if pre else 0)
+        self.L.conv_fwd(ctypes.byref(d), xin[0], w_ptr, bias_ptr, out[0], pre[0] if pre else None,
+                        aux[0] if aux else None, self.stream)
+
+    def wgrad_raw(self, geom, xin, dout, dw_ptr, wst):
+        N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+        d = self._desc(N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p, False, xin[1], dout[1], wst)
+        self.L.conv_wgrad(ctypes.byref(d), xin[0], dout[0], dw_ptr, self.stream)
+
+    def colsum(self, x, npix, C, out_ptr):
+        self.L.colsum(x[0], self.dt, x[1], npix, C, out_ptr, self.stream)
+
+    def copy_channels(self, src, dst, npix, C, acc=0):
+        self.L.copy_channels(src[0], src[1], dst[0], dst[1], self.dt, npix, C, acc, self.stream)
+
+
+# ------------------------------------------------------------------------------------------------
+# weight-stride helpers (element strides of the fp32 master weight for (out ch, in ch, ky, kx))
+# ------------------------------------------------------------------------------------------------
+
+def wst_conv(Co, Ci, k):          # nn.Conv2d / nn.Linear weight [Co, Ci, k, k]
+    return (Ci * k * k, k * k, k, 1)
+
+
+def wst_conv_T(Co, Ci, k):        # same weight seen from the input-gradient side: out ch = Ci, in ch = Co
+    return (k * k, Ci * k * k, k, 1)
+
+
+def wst_convT(Ci, Co, k):         # nn.ConvTranspose2d weight [Ci, Co, k, k], forward: out ch = Co
+    return (k * k, Co * k * k, k, 1)
+
+
+def wst_convT_T(Ci, Co, k):       # ConvTranspose2d input-gradient / weight-gradient view: out ch = Ci, in ch = Co
+    return (Co * k * k, k * k, k, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# Differentiable ops
+# ------------------------------------------------------------------------------------------------
+
+def conv2d(ctx: Ctx, x: Var, w: Param, b, k, stride=1, pad=0, act=ACT_NONE, out: Var = None, acc=0,
+           need_dx=True, keep_pre=False):
+    """nn.Conv2d / nn.Linear (k=1) forward with fused bias + activation.  If `act` is set the returned Var is
+    marked `fused_act`: consumers deliver its gradient already multiplied by act' (see conv dgrad / maxpool)."""
+    Co, Ci = w.data.shape[0], w.data.shape[1]
+    assert Ci == x.C, (w.name, Ci, x.C)
+    Ho = (x.H + 2 * pad - k) // stride + 1
+    Wo = (x.W + 2 * pad - k) // stride + 1
+    y = out if out is not None else ctx.new(x.N, Ho, Wo, Co)
+    assert (y.H, y.W, y.C) == (Ho, Wo, Co)
+    geom = (x.N, x.H, x.W, Ci, Ho, Wo, Co, k, stride, pad)
+    pre = None
+    if act == ACT_GELU or keep_pre:
+        pre = ctx.new(x.N, Ho, Wo, Co)
+    ctx.conv_raw(geom, (x.ptr, x.ld), w.ptr, wst_conv(Co, Ci, k), b.ptr if b is not None else None, (y.ptr, y.ld),
+                 act=act, acc=acc, pre=(pre.ptr, pre.ld) if pre is not None else None)
+    if act != ACT_NONE:
+        y.fused_act = (act, pre if act == ACT_GELU else y)
+    train_w = ctx.param_grads
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        if train_w:
+            ctx.wgrad_raw(geom, (x.ptr, x.ld), gi, w.gptr, wst_conv(Co, Ci, k))
+            if b is not None:
+                ctx.colsum(gi, y.npix, Co, b.gptr)
+        if need_dx:
+            conv2d_dgrad(ctx, x, gi, w, geom)
+    ctx.record(bwd)
+    return y
+
+
+def conv2d_dgrad(ctx, x: Var, gi, w: Param, geom):
+    """dx (=|+=) conv-transpose of the output gradient; applies x.fused_act' in the epilogue."""
+    N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+    gp, gld, gacc = x.grad_out()
+    dact, aux = (0, None)
+    if x.fused_act is not None:
+        dact, av = x.fused_act
+        aux = (av.ptr, av.ld)
+    g2 = (N, Ho, Wo, Co, Hi, Wi, Ci, k, s, p)
+    ctx.conv_raw(g2, gi, w.ptr, wst_conv_T(Co, Ci, k), None, (gp, gld), dact=dact, acc=gacc, aux=aux, transposed=True)
+
+
+def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
+    """nn.ConvTranspose2d(k=3, s=2, p=1, output_padding=1) forward (MixConvNeXtML.py:53,150)."""
+    Ci, Co, k = w.data.shape[0], w.data.shape[1], 3
+    assert Ci == x.C
+    Ho, Wo = 2 * x.H, 2 * x.W
+    y = ctx.new(x.N, Ho, Wo, Co)
+    gf = (x.N, x.H, x.W, Ci, Ho, Wo, Co, k, 2, 1)
+    ctx.conv_raw(gf, (x.ptr, x.ld), w.ptr, wst_convT(Ci, Co, k), b.ptr, (y.ptr, y.ld), transposed=True)
+    train_w = ctx.param_grads
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        # seen as a stride-2 conv from the (big) output gradient to the (small) input
+        gb = (x.N, Ho, Wo, Co, x.H, x.W, Ci, k, 2, 1)
+        if train_w:
+            ctx.wgrad_raw(gb, gi, (x.ptr, x.ld), w.gptr, wst_convT_T(Ci, Co, k))
+            ctx.colsum(gi, y.npix, Co, b.gptr)
+        gp, gld, gacc = x.grad_out()
+        assert x.fused_act is None
+        ctx.conv_raw(gb, gi, w.ptr, wst_convT_T(Ci, Co, k), None, (gp, gld), acc=gacc)
+    ctx.record(bwd)
+    return y
+
+
+def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=True):
+    """Depthwise k x k, stride 1, pad k//2 (MixConvNeXtML.py:94-97,220)."""
+    y = out if out is not None else ctx.new(x.N, x.H, x.W, x.C)
+    L, s = ctx.L, ctx.stream
+    L.dwconv_fwd(x.ptr, x.ld, w.ptr, b.ptr, y.ptr, y.ld, ctx.dt, x.N, x.H, x.W, x.C, k, 0, 0, s)
+    train_w = ctx.param_grads
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        if train_w:
+            L.dwconv_wgrad(x.ptr, x.ld, gi[0], gi[1], w.gptr, b.gptr, ctx.dt, x.N, x.H, x.W, x.C, k, ctx.stream)
+        if not need_dx:
+            return
+        gp, gld, gacc = x.grad_out()
+        assert x.fused_act is None
+        L.dwconv_fwd(gi[0], gi[1], w.ptr, None, gp, gld, ctx.dt, x.N, x.H, x.W, x.C, k, 1, gacc, ctx.stream)
+    ctx.record(bwd)
+    return y
+
+
+def inorm(ctx: Ctx, x: Var, act=ACT_NONE, res: Var = None, out: Var = None):
+    """y = act(InstanceNorm(x) + res); `out` may be a channel slice of a concat buffer."""
+    y = out if out is not None else ctx.new(x.N, x.H, x.W, x.C)
+    L = ctx.L
+    HW = x.H * x.W
+    stats = ctx.f32(x.N, x.C, 3)
+    L.inorm_stats(x.ptr, x.ld, ctx.dt, x.N, HW, x.C, stats.data_ptr(), ctx.stream)
+    rp, rld = (res.ptr, res.ld) if res is not None else (None, 0)
+    L.inorm_apply(x.ptr, x.ld, stats.data_ptr(), rp, rld, y.ptr, y.ld, ctx.dt, x.N, HW, x.C, act, ctx.stream)
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        bst = ctx.f32(x.N, x.C, 2)
+        L.inorm_bwd_stats(x.ptr, x.ld, stats.data_ptr(), rp, rld, gi[0], gi[1], ctx.dt, x.N, HW, x.C, act,
+                          bst.data_ptr(), ctx.stream)
+        gp, gld, gacc = x.grad_out()
+        assert x.fused_act is None
+        if res is not None:
+            qp, qld, qacc = res.grad_out()
+            assert res.fused_act is None
+        else:
+            qp, qld, qacc = None, 0, 0
+        L.inorm_bwd_apply(x.ptr, x.ld, stats.data_ptr(), rp, rld, gi[0], gi[1], bst.data_ptr(), gp, gld, gacc,
+                          qp, qld, qacc, ctx.dt, x.N, HW, x.C, act, ctx.stream)
+    ctx.record(bwd)
+    return y
+
+
+def maxpool(ctx: Ctx, x: Var, k):
+    y = ctx.new(x.N, x.H // k, x.W // k, x.C)
+    ctx.L.maxpool_fwd(x.ptr, x.ld, y.ptr, y.ld, ctx.dt, x.N, x.H, x.W, x.C, k, ctx.stream)
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        gp, gld, gacc = x.grad_out()
+        relu = 0
+        if x.fused_act is not None:
+            assert x.fused_act[0] == ACT_RELU, "maxpool backward only fuses the ReLU mask"
+            relu = 1
+        ctx.L.maxpool_bwd(x.ptr, x.ld, gi[0], gi[1], gp, gld, ctx.dt, x.N, x.H, x.W, x.C, k, gacc, relu, ctx.stream)
+    ctx.record(bwd)
+    return y
+
+
+def add_n(ctx: Ctx, xs):
+    """Sum of 2..5 same-shaped tensors (multi-scale skip sums, MixConvNeXtML.py:482-491)."""
+    x0 = xs[0]
+    assert all(v.ld == v.C for v in xs)
+    y = ctx.new(x0.N, x0.H, x0.W, x0.C)
+    ptrs = [v.ptr for v in xs] + [None] * (5 - len(xs))
+    ctx.L.add_n(y.ptr, ctx.dt, x0.npix * x0.C, *ptrs, ctx.stream)
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        for v in xs:
+            gp, gld, gacc = v.grad_out()
+            assert v.fused_act is None
+            ctx.copy_channels(gi, (gp, gld), v.npix, v.C, gacc)
+    ctx.record(bwd)
+    return y
+
+
+def concat_into(ctx: Ctx, cat: Var, coff, src: Var):
+    """cat[..., coff:coff+src.C] = src, with the matching slice-gradient routed back to src."""
+    dst = cat.slice(coff, src.C)
+    ctx.copy_channels((src.ptr, src.ld), (dst.ptr, dst.ld), src.npix, src.C, 0)
+
+    def bwd():
+        gi = dst.grad_in()
+        if gi is None:
+            return
+        gp, gld, gacc = src.grad_out()
+        assert src.fused_act is None
+        ctx.copy_channels(gi, (gp, gld), src.npix, src.C, gacc)
+    ctx.record(bwd)
+
+
+def ca_scale(ctx: Ctx, x: Var, fc1: Param, slope: Param, fc2: Param):
+    """y = x * CA(x)  (MixConvNeXtML.py:17-22,112)."""
+    N, C, HW = x.N, x.C, x.H * x.W
+    assert x.ld == x.C
+    L = ctx.L
+    avg, mx, s = ctx.f32(N, C), ctx.f32(N, C), ctx.f32(N, C)
+    am = torch.empty((N, C), dtype=torch.int32, device=ctx.device)
+    ws = torch.empty((N, C), dtype=torch.int64, device=ctx.device)
+    L.ca_fwd(x.ptr, ctx.dt, N, HW, C, fc1.ptr, slope.ptr, fc2.ptr, avg.data_ptr(), mx.data_ptr(), am.data_ptr(),
+             s.data_ptr(), ws.data_ptr(), ctx.stream)
+    y = ctx.new(N, x.H, x.W, C)
+    L.scale_nc_fwd(x.ptr, s.data_ptr(), y.ptr, ctx.dt, N, HW, C, ctx.stream)
+    train_w = ctx.param_grads
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        assert gi[1] == C
+        ds, davg, dmax = ctx.f32(N, C), ctx.f32(N, C), ctx.f32(N, C)
+        L.scale_nc_bwd_reduce(x.ptr, gi[0], ds.data_ptr(), ctx.dt, N, HW, C, ctx.stream)
+        if train_w:
+            d1, dsl, d2 = fc1.gptr, slope.gptr, fc2.gptr
+        else:
+            scratch = ctx.zeros_f32(fc1.data.numel() + 1 + fc2.data.numel())
+            d1 = scratch.data_ptr()
+            dsl = d1 + 4 * fc1.data.numel()
+            d2 = dsl + 4
+        L.ca_bwd(ds.data_ptr(), s.data_ptr(), avg.data_ptr(), mx.data_ptr(), N, C, fc1.ptr, slope.ptr, fc2.ptr,
+                 d1, dsl, d2, davg.data_ptr(), dmax.data_ptr(), ctx.stream)
+        gp, gld, gacc = x.grad_out()
+        assert gld == C and x.fused_act is None
+        L.scale_nc_bwd_apply(gi[0], s.data_ptr(), davg.data_ptr(), dmax.data_ptr(), am.data_ptr(), gp, ctx.dt, N, HW,
+                             C, gacc, ctx.stream)
+    ctx.record(bwd)
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# image <-> NHWC boundary
+# ------------------------------------------------------------------------------------------------
+
+def image_to_nhwc(ctx: Ctx, img: torch.Tensor, out: Var = None, scale=1.0, shift=0.0):
+    """NCHW fp32 image -> NHWC activation (optionally a channel slice, e.g. for cat(real_A, fake_B))."""
+    N, C, H, W = img.shape
+    assert img.dtype == torch.float32 and img.is_contiguous() and img.is_cuda
+    y = out if out is not None else ctx.new(N, H, W, C)
+    ctx.L.nchw_to_nhwc(img.data_ptr(), y.ptr, ctx.dt, N, C, H, W, y.ld, scale, shift, ctx.stream)
+    return y
+
+
+def nhwc_grad_to_image(ctx: Ctx, v: Var, dimg: torch.Tensor, alpha=1.0, acc=1):
+    """dimg (NCHW fp32) (=|+=) alpha * v.grad."""
+    gi = v.grad_in()
+    if gi is None:
+        return
+    ctx.L.nhwc_to_nchw(gi[0], ctx.dt, gi[1], dimg.data_ptr(), v.N, v.C, v.H, v.W, alpha, acc, ctx.stream)

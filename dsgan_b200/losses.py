@@ -1,0 +1,127 @@
+"""Loss graphs: GAN (BCE-with-logits / MSE), L1, VGG-feature L1, TV, SSIM and MS-SSIM — forward value and the
+gradient w.r.t. the generated image, written by the bandwidth kernels of csrc/loss.cu.
+
+Image-level tensors are NCHW fp32 (what the reference's API holds, pix2pix_model.py:129-139); loss values are
+accumulated into fp32 device scalars (`slot` pointers) with no host synchronisation.
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import ACT_RELU, ACT_SIGMOID, F32, Ctx, Var
+
+MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)  # MS_SSIM.py:200
+
+
+def gan_loss(ctx: Ctx, pred: Var, target_is_real: bool, slot: int, loss_scale=1.0, grad_scale=1.0, use_lsgan=False,
+             sigmoid_d=False, want_grad=True):
+    """GANLoss.__call__ (networks.py:154-163).  Writes d(loss*grad_scale)/d pred into pred's gradient."""
+    assert pred.ld == pred.C
+    n = pred.npix * pred.C
+    mode = 0 if not use_lsgan else (2 if sigmoid_d else 1)
+    gp = None
+    if want_grad and not ctx.no_grad:
+        gp, gld, gacc = pred.grad_out()
+        assert gacc == 0 and gld == pred.C and pred.fused_act is None
+    ctx.L.gan_loss(pred.ptr, ctx.dt, n, 1.0 if target_is_real else 0.0, mode, loss_scale, slot, grad_scale, gp,
+                   ctx.stream)
+
+
+def l1_images(ctx: Ctx, fake: torch.Tensor, real: torch.Tensor, slot: int, grad_scale, dfake: torch.Tensor):
+    """criterionL1(fake_B, real_B) (pix2pix_model.py:177); dfake += grad."""
+    ctx.L.l1_loss(fake.data_ptr(), real.data_ptr(), F32, fake.numel(), slot, grad_scale,
+                  dfake.data_ptr() if dfake is not None else None, 1, 0, ctx.stream)
+
+
+def l1_features(ctx: Ctx, f: Var, r: Var, slot: int, grad_scale):
+    """criterionL1 on one VGG tap (pix2pix_model.py:182-186); the tap is a fused-ReLU output, so its gradient is
+    kept w.r.t. the pre-activation (masked by f > 0)."""
+    assert f.ld == f.C and r.ld == r.C
+    gp, acc, relu = None, 0, 0
+    if not ctx.no_grad:
+        gp, _gld, acc = f.grad_out()
+        if f.fused_act is not None:
+            assert f.fused_act[0] == ACT_RELU
+            relu = 1
+    ctx.L.l1_loss(f.ptr, r.ptr, ctx.dt, f.npix * f.C, slot, grad_scale, gp, acc, relu, ctx.stream)
+
+
+def tv_loss(ctx: Ctx, fake: torch.Tensor, slot: int, grad_scale, dfake: torch.Tensor):
+    """TV loss with the reference's literal 320*256 divisor and batch SUM (pix2pix_model.py:189-191, Q10)."""
+    N, C, H, W = fake.shape
+    ctx.L.tv_loss(fake.data_ptr(), N * C, H, W, float(320 * 256), slot, grad_scale,
+                  dfake.data_ptr() if dfake is not None else None, ctx.stream)
+
+
+def _affine(ctx: Ctx, img: torch.Tensor, scale, shift):
+    out = torch.empty_like(img)
+    N, C, H, W = img.shape
+    ctx.L.nchw_to_nhwc(img.data_ptr(), out.data_ptr(), F32, N * C, 1, H, W, 1, scale, shift, ctx.stream)
+    return out
+
+
+def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, out_scale, dY: torch.Tensor = None,
+                        grad_scale=0.0, data_range=1.0, K=(0.01, 0.03), multiscale=False, per_plane=None):
+    """slot += out_scale * {ssim | ms_ssim}(X, Y)  (MS_SSIM.py:95-225, size_average=True) and, if dY is given,
+    dY += grad_scale * d value / dY.  X, Y: NCHW fp32 in [0, data_range].  `per_plane` (fp32 [L,NC,2]) receives
+    the raw per-plane map sums when given."""
+    N, C, H, W = X.shape
+    NC = N * C
+    L_ = ctx.L
+    C1, C2 = (K[0] * data_range) ** 2, (K[1] * data_range) ** 2
+    levels = 5 if multiscale else 1
+    if multiscale and min(H, W) <= 160:
+        raise AssertionError("Image size should be larger than 160 due to the 4 downsamplings in ms-ssim")
+    if min(H, W) < 11:
+        raise ValueError("ssim needs H, W >= 11 (win_size), got %dx%d" % (H, W))
+    sums = per_plane if per_plane is not None else ctx.f32(levels, NC, 2)
+    xs, ys, sizes = [X], [Y], []
+    for lv in range(levels):
+        h, w = xs[lv].shape[-2:]
+        L_.ssim_fwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, sums[lv].data_ptr(), ctx.stream)
+        sizes.append((h - 10) * (w - 10))
+        if lv < levels - 1:
+            if h % 2 or w % 2:
+                raise ValueError("ms_ssim: odd pyramid level %dx%d is not supported" % (h, w))
+            nx = torch.empty((N, C, h // 2, w // 2), dtype=torch.float32, device=X.device)
+            ny = torch.empty_like(nx)
+            L_.avgpool2_fwd(xs[lv].data_ptr(), nx.data_ptr(), NC, h, w, ctx.stream)
+            L_.avgpool2_fwd(ys[lv].data_ptr(), ny.data_ptr(), NC, h, w, ctx.stream)
+            xs.append(nx)
+            ys.append(ny)
+    want = dY is not None
+    coef = ctx.f32(levels, NC, 2) if want else None
+    if multiscale:
+        inv = torch.tensor([1.0 / s for s in sizes], dtype=torch.float32).to(X.device, non_blocking=True)
+        wts = torch.tensor(MS_WEIGHTS, dtype=torch.float32).to(X.device, non_blocking=True)
+        L_.msssim_combine(sums.data_ptr(), inv.data_ptr(), wts.data_ptr(), levels, NC, out_scale, slot, grad_scale,
+                          coef.data_ptr() if want else None, ctx.stream)
+    else:
+        L_.ssim_combine(sums.data_ptr(), 1.0 / sizes[0], NC, out_scale, slot, grad_scale,
+                        coef.data_ptr() if want else None, ctx.stream)
+    if not want:
+        return
+    # backward: coarsest level first, each level's dY folded into the next finer one through avg_pool's adjoint
+    g_next = None
+    for lv in reversed(range(levels)):
+        h, w = xs[lv].shape[-2:]
+        g = dY if lv == 0 else torch.empty_like(ys[lv])
+        L_.ssim_bwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, coef[lv].data_ptr(), g.data_ptr(),
+                    1 if lv == 0 else 0, ctx.stream)
+        if g_next is not None:
+            L_.avgpool2_bwd(g_next.data_ptr(), g.data_ptr(), NC, h, w, 1, ctx.stream)
+        g_next = g
+
+
+def ssim_training_loss(ctx: Ctx, real_B, fake_B, slot, w_ss, dfake):
+    """loss_ssim = 1 - ssim((real_B+1)/2, (fake_B+1)/2, data_range=1) (pix2pix_model.py:193-195); the slot must
+    start at 1.0.  dfake += w_ss * d loss / d fake_B."""
+    X, Y = _affine(ctx, real_B, 0.5, 0.5), _affine(ctx, fake_B, 0.5, 0.5)
+    dY = None
+    if dfake is not None:
+        dY = torch.empty_like(Y)
+        ctx.zero_(dY)
+    ssim_value_and_grad(ctx, X, Y, slot, -1.0, dY, grad_scale=-w_ss)
+    if dfake is not None:  # dfake += 0.5 * dY
+        N, C, H, W = Y.shape
+        ctx.L.nhwc_to_nchw(dY.data_ptr(), F32, 1, dfake.data_ptr(), N * C, 1, H, W, 0.5, 1, ctx.stream)

@@ -1,0 +1,196 @@
+"""Pix2PixModel with the reference's surface (DSGAN/models/pix2pix_model.py:61-310): initialize, set_input, forward,
+backward_D, backward_G, optimize_parameters, get_img_*.  Every tensor op below this file is a hand-written
+sm_100a kernel reached through the C ABI; orchestration stays in Python like the reference.
+
+Data parallelism (replaces nn.DataParallel, networks.py:77): one process per GPU; each rank runs this step on its
+batch shard and gradients are summed with NCCL over the networks' flat gradient buffers, then averaged inside
+the fused Adam (grad_scale = 1/world).  The TV term is a batch SUM in the reference (pix2pix_model.py:189-191),
+so its gradient is pre-scaled by `world` to keep R-rank training equal to single-GPU big-batch math.
+"""
+import torch
+import torch.distributed as dist
+
+from .. import losses
+from ..engine import image_to_nhwc, nhwc_grad_to_image
+from ..optim import FlatAdam
+from ..util.image_pool import ImagePool
+from . import networks
+from .base_model import BaseModel
+from .vgg import Vgg16
+
+SLOT = {"G_GAN": 0, "G_L1": 1, "vgg": 2, "tv": 3, "ssim": 4, "D_fake": 5, "D_real": 6}
+
+
+class Pix2PixModel(BaseModel):
+    def name(self):
+        return "Pix2PixModel"
+
+    @staticmethod
+    def modify_commandline_options(parser, is_train=True):
+        if is_train:
+            parser.add_argument("--lambda_L1", type=float, default=100.0, help="weight for L1 loss (unused, Q11)")
+        return parser
+
+    def initialize(self, opt):
+        BaseModel.initialize(self, opt)
+        self.precision = getattr(opt, "precision", "bf16")
+        self.loss_names = ["G_GAN", "G_L1", "D_real", "D_fake"]
+        self.visual_names = ["real_A", "fake_B", "real_B"]
+        self.model_names = ["G", "D"] if self.isTrain else ["G"]
+        self.use_gan, self.use_condition = opt.use_GAN, opt.use_condition
+        self.w_vgg, self.w_tv, self.w_gan, self.w_ss = opt.w_vgg, opt.w_tv, opt.w_gan, opt.w_ss
+        networks.KernelNet.precision = self.precision
+        self.netG = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.which_model_netG, opt.norm,
+                                      not opt.no_dropout, opt.init_type, self.gpu_ids)
+        self.ctx = networks.get_ctx(self.device, self.precision)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.isTrain:
+            use_sigmoid = opt.no_lsgan
+            d_in = opt.input_nc + opt.output_nc if self.use_condition == 1 else opt.input_nc
+            self.netD = networks.define_D(d_in, opt.ndf, opt.which_model_netD, opt.n_layers_D, opt.norm, use_sigmoid,
+                                          opt.init_type, self.gpu_ids)
+            self.fake_AB_pool = ImagePool(opt.pool_size)
+            self.use_lsgan = opt.no_lsgan  # the reference's inverted flag (pix2pix_model.py:98,112-114, Q6)
+            self.criterionGAN = networks.GANLoss(use_lsgan=opt.no_lsgan).to(self.device)
+            self.vgg = Vgg16().to(self.device)
+            self.optimizer_G = FlatAdam(self.netG, lr=opt.lr, betas=(opt.beta1, 0.999))
+            self.optimizer_D = FlatAdam(self.netD, lr=opt.lr, betas=(opt.beta1, 0.999))
+            self.optimizers = [self.optimizer_G, self.optimizer_D]
+            self._loss = torch.zeros(8, dtype=torch.float32, device=self.device)
+            init = torch.zeros(8, dtype=torch.float32)
+            init[SLOT["ssim"]] = 1.0  # loss_ssim = 1 - ssim
+            self._loss_init = init.to(self.device)
+            if self.world > 1:  # identical replicas: rank 0's initial weights everywhere
+                for net in (self.netG, self.netD, self.vgg):
+                    dist.broadcast(net.flat_buffers()[0], 0)
+
+    # ---- reference API ---------------------------------------------------------------------
+    def set_input(self, input):
+        AtoB = self.opt.which_direction == "AtoB"
+        self.real_A = input["A" if AtoB else "B"].to(self.device, non_blocking=True).float().contiguous()
+        self.real_B = input["B" if AtoB else "A"].to(self.device, non_blocking=True).float().contiguous()
+        self.image_paths = input["A_paths" if AtoB else "B_paths"]
+
+    def forward(self):
+        self.ctx.clear()
+        self.fake_B = self.netG(self.real_A)
+        self._g_out = self.netG.last_output
+        self._g_tape = self.ctx.take_tape()
+
+    def _slot(self, name):
+        return self._loss.data_ptr() + 4 * SLOT[name]
+
+    def _pair(self, a, b):
+        """cat((a, b), 1) as one NHWC tensor (pix2pix_model.py:145,153,168)."""
+        N, C, H, W = a.shape
+        v = self.ctx.new(N, H, W, C + b.shape[1])
+        image_to_nhwc(self.ctx, a, out=v.slice(0, C))
+        image_to_nhwc(self.ctx, b, out=v.slice(C, b.shape[1]))
+        return v
+
+    def _gan_kw(self):
+        return dict(use_lsgan=self.use_lsgan, sigmoid_d=self.use_lsgan)
+
+    def backward_D(self):
+        ctx = self.ctx
+        ctx.param_grads = True
+        if self.use_condition == 1:
+            fake_AB = self.fake_AB_pool.query(torch.cat((self.real_A, self.fake_B), 1))
+            xf = image_to_nhwc(ctx, fake_AB.contiguous())
+            xr = self._pair(self.real_A, self.real_B)
+        else:
+            xf, xr = image_to_nhwc(ctx, self.fake_B), image_to_nhwc(ctx, self.real_B)
+        pred_fake = self.netD.forward_var(xf, need_dx=False)
+        losses.gan_loss(ctx, pred_fake, False, self._slot("D_fake"), 1.0, 0.5, **self._gan_kw())
+        pred_real = self.netD.forward_var(xr, need_dx=False)
+        losses.gan_loss(ctx, pred_real, True, self._slot("D_real"), 1.0, 0.5, **self._gan_kw())
+        ctx.backward()  # loss_D = 0.5*(fake+real)
+
+    def backward_G(self):
+        ctx = self.ctx
+        fake, real = self.fake_B, self.real_B
+        dfake = torch.empty_like(fake)
+        ctx.zero_(dfake)
+        ctx.param_grads = False  # D and VGG are frozen here (set_requires_grad(netD, False), vgg.py:27-28)
+        if self.use_gan == 1:
+            x = self._pair(self.real_A, fake) if self.use_condition == 1 else image_to_nhwc(ctx, fake)
+            pred = self.netD.forward_var(x, need_dx=True)
+            losses.gan_loss(ctx, pred, True, self._slot("G_GAN"), 1.0, float(self.w_gan), **self._gan_kw())
+            ctx.backward()
+            gv = x.slice(self.real_A.shape[1], fake.shape[1]) if self.use_condition == 1 else x
+            nhwc_grad_to_image(ctx, gv, dfake)
+        losses.l1_images(ctx, fake, real, self._slot("G_L1"), 1.0, dfake)
+        # VGG perceptual loss on raw [-1,1] images (pix2pix_model.py:180-186, Q14)
+        ctx.no_grad = True
+        fr = self.vgg.forward_var(image_to_nhwc(ctx, real), need_dx=False)
+        ctx.no_grad = False
+        xv = image_to_nhwc(ctx, fake)
+        ff = self.vgg.forward_var(xv, need_dx=True)
+        for f, r in zip(ff, fr):
+            losses.l1_features(ctx, f, r, self._slot("vgg"), float(self.w_vgg))
+        ctx.backward()
+        nhwc_grad_to_image(ctx, xv, dfake)
+        losses.tv_loss(ctx, fake, self._slot("tv"), float(self.w_tv) * self.world, dfake)
+        losses.ssim_training_loss(ctx, real, fake, self._slot("ssim"), float(self.w_ss), dfake)
+        # dL/dfake_B -> generator backward
+        ctx.param_grads = True
+        gp, _ld, _acc = self._g_out.grad_out()
+        ctx.L.nchw_to_nhwc(dfake.data_ptr(), gp, ctx.dt, fake.shape[0], fake.shape[1], fake.shape[2], fake.shape[3],
+                           self._g_out.C, 1.0, 0.0, ctx.stream)
+        ctx.backward(self._g_tape)
+        self._g_tape = self._g_out = None
+
+    def _allreduce(self, net):
+        if self.world > 1:
+            dist.all_reduce(net.flat_buffers()[1], op=dist.ReduceOp.SUM)
+
+    def optimize_parameters(self):
+        self._loss.copy_(self._loss_init)
+        self.forward()
+        if self.use_gan == 1:
+            self.set_requires_grad(self.netD, True)
+            self.optimizer_D.zero_grad()
+            self.backward_D()
+            self._allreduce(self.netD)
+            self.optimizer_D.step(1.0 / self.world)
+        self.set_requires_grad(self.netD, False)
+        self.optimizer_G.zero_grad()
+        self.backward_G()
+        self._allreduce(self.netG)
+        self.optimizer_G.step(1.0 / self.world)
+
+    # ---- loss attributes (0-d device tensors; float() synchronises, like the reference's) -----
+    def __getattr__(self, name):
+        if name.startswith("loss_") or name == "tv_loss":
+            L = self.__dict__.get("_loss")
+            if L is not None:
+                key = name[5:] if name.startswith("loss_") else "tv"
+                if key in SLOT:
+                    return L[SLOT[key]]
+                if key == "G":
+                    return (L[SLOT["G_GAN"]] * self.w_gan + L[SLOT["G_L1"]] + L[SLOT["vgg"]] * self.w_vgg
+                            + L[SLOT["tv"]] * self.w_tv + L[SLOT["ssim"]] * self.w_ss)
+                if key == "D":
+                    return (L[SLOT["D_fake"]] + L[SLOT["D_real"]]) * 0.5
+        raise AttributeError(name)
+
+    # ---- host-side helpers of train.py (pix2pix_model.py:292-310) ----------------------------
+    def get_img_tir(self, input):
+        self.real_A = input["A"].to(self.device).float().contiguous()
+        return ((self.real_A + 1) / 2) * 255
+
+    def get_img_gen(self, input):
+        AtoB = self.opt.which_direction == "AtoB"
+        self.real_B = input["B" if AtoB else "A"].to(self.device).float().contiguous()
+        self.test()
+        return ((self.fake_B + 1) / 2) * 255
+
+    def get_img_label(self, input):
+        AtoB = self.opt.which_direction == "AtoB"
+        self.real_B = input["B" if AtoB else "A"].to(self.device).float().contiguous()
+        return ((self.real_B + 1) / 2) * 255
+
+    def get_img_nir(self, input):
+        AtoB = self.opt.which_direction == "AtoB"
+        self.real_A = input["A" if AtoB else "B"].to(self.device).float().contiguous()
+        return ((self.real_A + 1) / 2) * 255

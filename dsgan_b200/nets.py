@@ -1,0 +1,194 @@
+"""The three networks of the hot path as kernel graphs over the engine, plus the nn.Module shells that hold
+their parameters under the reference's names.
+
+G: MixConvNeXtML (models/model/MixConvNeXtML.py:428-494)   D: NLayerDiscriminator (networks.py:533-579)
+VGG16 taps (models/vgg.py:5-42).  The graphs are hand-scheduled: forward issues the kernels, and records on
+the engine tape the backward kernels each layer needs.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import specs
+from .engine import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, Ctx, Param, Var, add_n, ca_scale, concat_into, conv2d,
+                     conv_transpose2d, dwconv, image_to_nhwc, inorm, maxpool)
+
+
+class ParamTree(nn.Module):
+    """nn.Module whose parameters carry the reference's dotted names and live as views of one flat fp32 buffer
+    (so Adam, the bf16 shadow copy and the NCCL all-reduce each touch a single contiguous range)."""
+
+    def __init__(self, spec):
+        super().__init__()
+        self._spec = list(spec)
+        self._numel = sum(math.prod(s) for _n, s in self._spec)
+        flat = torch.zeros(self._numel)
+        off = 0
+        for name, shape in self._spec:
+            n = math.prod(shape)
+            mod = self
+            *path, leaf = name.split(".")
+            for part in path:
+                if not hasattr(mod, part):
+                    mod.add_module(part, nn.Module())
+                mod = getattr(mod, part)
+            mod.register_parameter(leaf, nn.Parameter(flat[off:off + n].view(shape)))
+            off += n
+        self._flat = flat
+        self._flat_grad = None
+        self._plist = None
+
+    def init_normal(self, gain=0.02):
+        """networks.init_weights('normal') (networks.py:49-70): Conv*/Linear weights N(0,gain), biases 0,
+        PReLU slope untouched (0.25)."""
+        for name, p in self.named_parameters():
+            if name.endswith("relu1.weight"):
+                p.data.fill_(0.25)
+            elif name.endswith(".bias"):
+                p.data.zero_()
+            else:
+                p.data.normal_(0.0, gain)
+        return self
+
+    def flat_buffers(self):
+        """(flat params, flat grads, {name: Param}); re-flattens if .to()/.cuda() replaced the storages."""
+        params = dict(self.named_parameters())
+        first = params[self._spec[0][0]]
+        dev = first.device
+        ok = self._flat.device == dev and self._flat_grad is not None and self._flat_grad.device == dev
+        if ok:
+            off = 0
+            for name, shape in self._spec:
+                if params[name].data_ptr() != self._flat.data_ptr() + 4 * off:
+                    ok = False
+                    break
+                off += math.prod(shape)
+        if not ok:
+            flat = torch.empty(self._numel, dtype=torch.float32, device=dev)
+            grad = torch.zeros(self._numel, dtype=torch.float32, device=dev)
+            off = 0
+            for name, shape in self._spec:
+                n = math.prod(shape)
+                flat[off:off + n].copy_(params[name].data.reshape(-1).float())
+                params[name].data = flat[off:off + n].view(shape)
+                params[name].grad = grad[off:off + n].view(shape)
+                off += n
+            self._flat, self._flat_grad, self._plist = flat, grad, None
+        if self._plist is None:
+            self._plist = {n: Param(n, p.data, p.grad) for n, p in params.items()}
+        return self._flat, self._flat_grad, self._plist
+
+
+# ------------------------------------------------------------------------------------------------
+# Generator graph
+# ------------------------------------------------------------------------------------------------
+
+def _block(ctx: Ctx, P, p, x: Var, out: Var = None, need_dx=True):
+    """ConvNeXt Block (MixConvNeXtML.py:230-243): dw7x7 -> IN -> Linear(C,4C) -> GELU -> Linear(4C,P) (+) 1x1 shortcut."""
+    t = dwconv(ctx, x, P[p + ".dwconv.weight"], P[p + ".dwconv.bias"], 7, need_dx=need_dx)
+    t = inorm(ctx, t)
+    h = conv2d(ctx, t, P[p + ".pwconv1.weight"], P[p + ".pwconv1.bias"], 1, act=ACT_GELU)
+    y = conv2d(ctx, h, P[p + ".pwconv2.weight"], P[p + ".pwconv2.bias"], 1, out=out)
+    conv2d(ctx, x, P[p + ".shortcut.weight"], None, 1, out=y, acc=1, need_dx=need_dx)
+    return y
+
+
+def _upsample(ctx: Ctx, P, p, x: Var, skip: Var):
+    """upSample (MixConvNeXtML.py:60-66): ConvT -> IN -> GELU written straight into the concat buffer."""
+    t = conv_transpose2d(ctx, x, P[p + ".weight"], P[p + ".bias"])
+    cat = ctx.new(t.N, t.H, t.W, t.C + skip.C)
+    inorm(ctx, t, act=ACT_GELU, out=cat.slice(0, t.C))
+    concat_into(ctx, cat, t.C, skip)
+    return cat
+
+
+def _downskip(ctx: Ctx, P, name, x: Var, k):
+    """MaxPool(k) -> 1x1 (no bias) -> IN -> GELU (MixConvNeXtML.py:328-426)."""
+    return inorm(ctx, conv2d(ctx, maxpool(ctx, x, k), P[name + ".1.weight"], None, 1), act=ACT_GELU)
+
+
+def _midmlka(ctx: Ctx, P, p, x: Var):
+    """MidMLKA (MixConvNeXtML.py:109-117)."""
+    q = x.C // 4
+    cat = ctx.new(x.N, x.H, x.W, x.C)
+    for i, k in enumerate((3, 5, 7, 9)):
+        dwconv(ctx, x.slice(i * q, q), P["%s.X%d.weight" % (p, k)], P["%s.X%d.bias" % (p, k)], k,
+               out=cat.slice(i * q, q))
+    o = conv2d(ctx, cat, P[p + ".conv.weight"], P[p + ".conv.bias"], 1)
+    o = ca_scale(ctx, o, P[p + ".attn.fc1.weight"], P[p + ".attn.relu1.weight"], P[p + ".attn.fc2.weight"])
+    return inorm(ctx, o, act=ACT_GELU, res=x)  # IN, then += x, then GELU (Q3)
+
+
+def _local(ctx: Ctx, P, x: Var):
+    """OriginMLKA (MixConvNeXtML.py:161-189)."""
+    L = "local."
+    d1 = conv2d(ctx, x, P[L + "to32.weight"], None, 1, need_dx=False)
+    d2 = _midmlka(ctx, P, L + "mid32", maxpool(ctx, d1, 2))
+    d3 = conv2d(ctx, d2, P[L + "to64.weight"], None, 1)
+    d4 = _midmlka(ctx, P, L + "mid64", maxpool(ctx, d3, 2))
+    d5 = conv2d(ctx, d4, P[L + "to128.weight"], None, 1)
+    d6 = _midmlka(ctx, P, L + "mid128", maxpool(ctx, d5, 2))
+    d7 = conv2d(ctx, d6, P[L + "to256.weight"], None, 1)
+    d8 = _midmlka(ctx, P, L + "mid256", maxpool(ctx, d7, 2))
+    u1 = _midmlka(ctx, P, L + "upc1.1", conv2d(ctx, _upsample(ctx, P, L + "up1.model.0", d8, d6),
+                                               P[L + "upc1.0.weight"], None, 1))
+    u2 = _midmlka(ctx, P, L + "upc2", _upsample(ctx, P, L + "up2.model.0", u1, d4))
+    u3 = _midmlka(ctx, P, L + "upc3", _upsample(ctx, P, L + "up3.model.0", u2, d3))
+    u4 = inorm(ctx, conv_transpose2d(ctx, u3, P[L + "up4.0.weight"], P[L + "up4.0.bias"]))
+    sc = conv2d(ctx, x, P[L + "shortcut.0.weight"], None, 1, need_dx=False)
+    return inorm(ctx, sc, act=ACT_GELU, res=u4)  # GELU(IN(up4) + IN(shortcut))
+
+
+def generator_forward(ctx: Ctx, P, x: Var) -> Var:
+    """MixConvNeXtML.forward (MixConvNeXtML.py:461-494) -> NHWC 3-channel output Var."""
+    if x.H % 16 or x.W % 16:
+        raise ValueError("MixConvNeXtML needs H and W to be multiples of 16, got %dx%d" % (x.H, x.W))
+    R, t = [], x
+    for i, (name, _cin, _cout) in enumerate(specs.ENC):
+        t = _block(ctx, P, name, t if i == 0 else maxpool(ctx, t, 2), need_dx=i > 0)
+        R.append(t)
+    R1, R2, R3, R4, R5 = R
+    # pyramid[level] collects the down-skip tensors landing on that decoder level
+    lvl = {16: [R5], 8: [], 4: [], 2: []}
+    for (mod, _cin, branches), src in zip(specs.SKIPS, (R1, R2, R3, R4)):
+        for br, k, _cout in branches:
+            scale = (x.H // src.H) * k          # total down-sampling w.r.t. the input
+            lvl[scale].append(_downskip(ctx, P, "%s.%s" % (mod, br), src, k))
+    o = add_n(ctx, lvl[16])
+    for (up, blk, _cin, _cout), skip, s in zip(specs.DEC, (R4, R3, R2, R1), (8, 4, 2, None)):
+        o = _block(ctx, P, blk, _upsample(ctx, P, up + ".model.0", o, skip))
+        if s is not None:
+            o = add_n(ctx, [o] + lvl[s])
+    loc = _local(ctx, P, x)
+    return conv2d(ctx, add_n(ctx, [o, loc]), P["res.weight"], P["res.bias"], 3, pad=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# Discriminator / VGG graphs
+# ------------------------------------------------------------------------------------------------
+
+def discriminator_forward(ctx: Ctx, P, x: Var, need_dx=True) -> Var:
+    """NLayerDiscriminator (networks.py:543-579): logits N x 30 x 30 x 1 (NHWC)."""
+    h = conv2d(ctx, x, P["model.0.weight"], P["model.0.bias"], 4, 2, 1, act=ACT_LEAKY, need_dx=need_dx)
+    for m, st in specs.D_LAYERS[1:4]:
+        h = conv2d(ctx, h, P["model.%d.weight" % m], P["model.%d.bias" % m], 4, st, 1)
+        h = inorm(ctx, h, act=ACT_LEAKY)
+    return conv2d(ctx, h, P["model.11.weight"], P["model.11.bias"], 4, 1, 1)
+
+
+def vgg_forward(ctx: Ctx, P, x: Var, need_dx=True):
+    """Vgg16 taps relu1_2, relu2_2, relu3_3, relu4_3 (vgg.py:30-38); weights are frozen (vgg.py:27-28)."""
+    taps, h, first = [], x, True
+    for e in specs.VGG_PLAN:
+        if e == "T":
+            taps.append(h)
+        elif e == "P":
+            h = maxpool(ctx, h, 2)
+        else:
+            h = conv2d(ctx, h, P[e[0] + ".weight"], P[e[0] + ".bias"], 3, 1, 1, act=ACT_RELU,
+                       need_dx=need_dx or not first)
+            first = False
+    return taps

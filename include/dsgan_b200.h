@@ -1,0 +1,182 @@
+/* dsgan_b200 — C ABI of the B200-native (sm_100a) kernels behind DS-GAN's adversarial training step.
+ *
+ * The reference (yglbgyx/DS-GAN) has no FFI: its extension point is the Python model/network API
+ * (DSGAN/models/__init__.py:4-37, networks.py:81-163, MS_SSIM.py:95-225) and every op below that API is
+ * a torch library call.  This header is the boundary a maintainer binds instead of those calls; each
+ * entry cites the reference op site it replaces (paths under DSGAN/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless stated; `stream` is a
+ *    cudaStream_t passed as void*.  The library never allocates or frees device memory and never
+ *    synchronises.  Return 0 on success, non-zero on failure (see dsgan_last_error()).
+ *  - activations are NHWC ("channels last"): element (n,y,x,c) of a tensor with pixel pitch `ld`
+ *    lives at ((n*H+y)*W+x)*ld + c.  `dtype` selects the activation element type: 0 = fp32
+ *    (validation mode), 1 = bf16 (production).  Parameters and parameter gradients are always fp32
+ *    in the reference's own layouts (OIHW conv, IOHW transposed conv, (out,in) linear).
+ *  - image-level tensors exchanged with the host API (real_A, real_B, fake_B, d fake_B) are NCHW fp32,
+ *    exactly what the reference's set_input / forward hold (pix2pix_model.py:129-139).
+ *  - there is NO CPU fallback: every entry point fails on a non-sm_100 device.
+ */
+#ifndef DSGAN_B200_H
+#define DSGAN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSGAN_ABI_VERSION 1
+
+enum { DSGAN_F32 = 0, DSGAN_BF16 = 1 };
+enum { DSGAN_ACT_NONE = 0, DSGAN_ACT_RELU = 1, DSGAN_ACT_LEAKY = 2, DSGAN_ACT_GELU = 3, DSGAN_ACT_SIGMOID = 4 };
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+int dsgan_abi_version(void);
+const char* dsgan_last_error(void);
+/* 0 iff the current device is sm_100 (B200); otherwise sets the error string. */
+int dsgan_device_check(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long dsgan_launch_count(void);
+int dsgan_memset(void* p, int byte_value, size_t bytes, void* stream);
+
+/* ---- layout / elementwise ------------------------------------------------------------------ */
+/* dst[n,y,x,c] = src[n,c,y,x]*scale + shift.  Replaces the implicit NCHW->kernel layout of
+ * `input['A'].to(device)` (pix2pix_model.py:131-132) and torch.cat((real_A, fake_B),1) (:145,:153,:168)
+ * when called twice into channel slices of one NHWC buffer. */
+int dsgan_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int C, int H, int W, int ld_dst,
+                       float scale, float shift, void* stream);
+/* dst[n,c,y,x] (fp32) = alpha*src[n,y,x,c] (+ dst if accumulate). */
+int dsgan_nhwc_to_nchw(const void* src, int dtype, int ld_src, float* dst, int N, int C, int H, int W,
+                       float alpha, int accumulate, void* stream);
+/* dst[p, 0:C] (=|+=) src[p, 0:C] for npix pixels with independent pitches: torch.cat / slicing and their
+ * backward (MixConvNeXtML.py:66,110). */
+int dsgan_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int dtype, long long npix, int C,
+                        int accumulate, void* stream);
+/* out = a + b (+ c + d + e): the multi-scale skip sums (MixConvNeXtML.py:482-491). Unused inputs NULL. */
+int dsgan_add_n(void* out, int dtype, long long n, const void* a, const void* b, const void* c, const void* d,
+                const void* e, void* stream);
+/* y[n,p,c] = x[n,p,c] * s[n,c]  (out * CA(out), MixConvNeXtML.py:112);  s is fp32 [N,C]. */
+int dsgan_scale_nc_fwd(const void* x, const float* s, void* y, int dtype, int N, long long HW, int C, void* stream);
+/* ds[n,c] = sum_p dy*x  (fp32, overwritten). */
+int dsgan_scale_nc_bwd_reduce(const void* x, const void* dy, float* ds, int dtype, int N, long long HW, int C,
+                              void* stream);
+/* dx = dy*s + davg[n,c]/HW + (p == argmax[n,c]) * dmax[n,c]   (=|+=) : backward of out*CA(out) including the
+ * adaptive avg/max pooling inside CA (MixConvNeXtML.py:7-8,18-19). */
+int dsgan_scale_nc_bwd_apply(const void* dy, const float* s, const float* davg, const float* dmax,
+                             const int* argmax, void* dx, int dtype, int N, long long HW, int C, int accumulate,
+                             void* stream);
+
+/* ---- dense convolution family (CUDA-core implicit GEMM; fp32 validation + odd shapes) ------ */
+typedef struct {
+  int dtype;
+  int N, Hi, Wi, Ci; /* input  tensor, pixel pitch ld_in  */
+  int Ho, Wo, Co;    /* output tensor, pixel pitch ld_out */
+  int kh, kw, stride, pad;
+  /* 0: out[o]  = sum_k in[o*stride - pad + k] * w   (nn.Conv2d forward; ConvTranspose2d input-gradient)
+   * 1: out[o]  = sum_k in[(o + pad - k)/stride] * w (nn.ConvTranspose2d forward; Conv2d input-gradient) */
+  int transposed;
+  int ld_in, ld_out, ld_aux, ld_pre;
+  long long w_sco, w_sci, w_sky, w_skx; /* element strides of the fp32 weight for (out ch, in ch, ky, kx) */
+  int act;        /* DSGAN_ACT_* applied last                                   */
+  int dact;       /* multiply by act'(aux) before `act` (backward through an activation) */
+  int accumulate; /* add the previous contents of `out` before dact/act           */
+} dsgan_conv_desc;
+/* v = sum + bias (+ out) ; v *= dact'(aux) ; pre_out = v ; out = act(v).
+ * Replaces nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward and input-gradient:
+ * MixConvNeXtML.py:53,122-159,218,222-224,335-425,459; networks.py:544-569; models/vgg.py:16-25. */
+int dsgan_conv_fwd(const dsgan_conv_desc* d, const void* in, const float* w, const float* bias, void* out,
+                   void* pre_out, const void* aux, void* stream);
+/* dw[co,ci,ky,kx] += sum_{n,oy,ox} dout[n,oy,ox,co] * in[n, oy*stride-pad+ky, ox*stride-pad+kx, ci]
+ * (d->N,Hi,Wi,Ci describe `in`; Ho,Wo,Co describe `dout`; `transposed` ignored). Weight gradient of the
+ * same op sites. */
+int dsgan_conv_wgrad(const dsgan_conv_desc* d, const void* in, const void* dout, float* dw, void* stream);
+/* out[c] += sum_p x[p,c]: bias gradients. */
+int dsgan_colsum(const void* x, int dtype, int ld, long long npix, int C, float* out, void* stream);
+
+/* ---- depthwise convolution (MixConvNeXtML.py:94-97,220: k = 3,5,7,9, stride 1, pad k/2) ---- */
+/* flip=0: forward (w is [C,1,k,k] fp32, bias may be NULL); flip=1: input-gradient (correlate with the
+ * flipped kernel, no bias). */
+int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias, void* y, int ld_y, int dtype,
+                     int N, int H, int W, int C, int k, int flip, int accumulate, void* stream);
+/* dw[c,ky,kx] += sum dy*x_shifted ; db[c] += sum dy  (db may be NULL). */
+int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float* dw, float* db, int dtype,
+                       int N, int H, int W, int C, int k, void* stream);
+
+/* ---- InstanceNorm2d(affine=False, eps=1e-5) fused with activation / residual ---------------- */
+/* stats[n,c] = {shift, sum(x-shift), sum((x-shift)^2)} (fp32 [N,C,3], overwritten).  networks.py:25. */
+int dsgan_inorm_stats(const void* x, int ld_x, int dtype, int N, long long HW, int C, float* stats, void* stream);
+/* y = act( (x-mean)*rstd + res ).  Covers IN, IN+GELU (+concat slice via ld_y), IN+LeakyReLU, and
+ * `IN(out) += x; GELU` (MixConvNeXtML.py:54,113-115,186-188,221,335-338; networks.py:556-566). res may be NULL. */
+int dsgan_inorm_apply(const void* x, int ld_x, const float* stats, const void* res, int ld_res, void* y, int ld_y,
+                      int dtype, int N, long long HW, int C, int act, void* stream);
+/* bstats[n,c] = {sum g, sum g*xhat}, g = dy*act'(xhat+res)  (fp32 [N,C,2], overwritten). */
+int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const void* res, int ld_res, const void* dy,
+                          int ld_dy, int dtype, int N, long long HW, int C, int act, float* bstats, void* stream);
+/* dx (=|+=) rstd*(g - mean(g) - xhat*mean(g*xhat));  dres (=|+=) g  (dres may be NULL). */
+int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const void* res, int ld_res, const void* dy,
+                          int ld_dy, const float* bstats, void* dx, int ld_dx, int acc_dx, void* dres, int ld_dres,
+                          int acc_dres, int dtype, int N, long long HW, int C, int act, void* stream);
+
+/* ---- pooling ------------------------------------------------------------------------------- */
+/* nn.MaxPool2d(k) (stride k), MixConvNeXtML.py:68-74,333-354; models/vgg.py pools. */
+int dsgan_maxpool_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int N, int H, int W, int C, int k,
+                      void* stream);
+/* dx (=|+=) dy routed to the first maximum in scan order; if relu_mask, the result is then multiplied by (x>0). */
+int dsgan_maxpool_bwd(const void* x, int ld_x, const void* dy, int ld_dy, void* dx, int ld_dx, int dtype, int N,
+                      int H, int W, int C, int k, int accumulate, int relu_mask, void* stream);
+/* AdaptiveAvgPool2d(1) + AdaptiveMaxPool2d(1) + fc1 -> PReLU -> fc2 (shared) -> add -> sigmoid
+ * (CA.forward, MixConvNeXtML.py:17-22).  avg,mx,s: fp32 [N,C]; argmax int32 [N,C] (pixel index);
+ * fc1 [C/8,C], fc2 [C,C/8], slope [1]. */
+int dsgan_ca_fwd(const void* x, int dtype, int N, long long HW, int C, const float* fc1, const float* slope,
+                 const float* fc2, float* avg, float* mx, int* argmax, float* s, void* workspace /* >= 8*N*C bytes */,
+                 void* stream);
+/* given ds [N,C]: dfc1,dfc2,dslope += ; davg,dmax [N,C] overwritten. */
+int dsgan_ca_bwd(const float* ds, const float* s, const float* avg, const float* mx, int N, int C, const float* fc1,
+                 const float* slope, const float* fc2, float* dfc1, float* dslope, float* dfc2, float* davg,
+                 float* dmax, void* stream);
+
+/* ---- losses --------------------------------------------------------------------------------- */
+/* GANLoss (networks.py:143-163): mode 0 = BCEWithLogits, 1 = MSE, 2 = MSE on sigmoid(pred) (the `--no_lsgan`
+ * pairing of Sigmoid-D + MSELoss, pix2pix_model.py:98,112-114); target is the constant 1.0/0.0.
+ * loss[0] += loss_scale*mean(...);  dpred (=) grad_scale * d mean/d pred  (dpred may be NULL). */
+int dsgan_gan_loss(const void* pred, int dtype, long long n, float target, int mode, float loss_scale, float* loss,
+                   float grad_scale, void* dpred, void* stream);
+/* nn.L1Loss (pix2pix_model.py:115,177,182-186): loss[0] += mean|a-b|; da (=|+=) grad_scale*sign(a-b)/n,
+ * multiplied by (a>0) when relu_mask (a is a ReLU output whose gradient is kept w.r.t. its pre-activation). */
+int dsgan_l1_loss(const void* a, const void* b, int dtype, long long n, float* loss, float grad_scale, void* da,
+                  int accumulate, int relu_mask, void* stream);
+/* TV loss (pix2pix_model.py:189-191) on NCHW fp32: loss[0] += (sum|dx|+sum|dy|)/denom; dx (+=) grad_scale*d/dx. */
+int dsgan_tv_loss(const float* x, int NC, int H, int W, float denom, float* loss, float grad_scale, float* dx,
+                  void* stream);
+/* _ssim (MS_SSIM.py:55-92) on NCHW fp32 planes, 11-tap Gaussian, valid padding.
+ * sums[nc] = {sum ssim_map, sum cs_map} (fp32 [NC,2], overwritten). X is the first argument of the reference
+ * call (real), Y the second (fake). */
+int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, float* sums,
+                   void* stream);
+/* dY (=|+=) sum over windows of coef[nc]={g_ssim,g_cs} . d{ssim_map,cs_map}/dY (coef: fp32 [NC,2], already
+ * divided by the map size). */
+int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, const float* coef,
+                   float* dY, int accumulate, void* stream);
+/* F.avg_pool2d(k=2) on NCHW fp32 planes (MS_SSIM.py:214-216) and its backward (dx += dy/4). */
+int dsgan_avgpool2_fwd(const float* x, float* y, int NC, int H, int W, void* stream);
+int dsgan_avgpool2_bwd(const float* dy, float* dx, int NC, int H, int W, int accumulate, void* stream);
+/* ms_ssim combine (MS_SSIM.py:218-225): sums [L,NC,2], sizes[L] = map pixel count, weights[L].
+ * val[0] += out_scale * mean_nc prod_l relu(v_l)^w_l ; coef [L,NC,2] = grad_scale * d val / d sums. */
+int dsgan_msssim_combine(const float* sums, const float* inv_sizes, const float* weights, int L, int NC,
+                         float out_scale, float* val, float grad_scale, float* coef, void* stream);
+/* single-scale: val[0] += out_scale*mean_nc(ssim) ; coef[nc] = {grad_scale/(NC*size), 0}. */
+int dsgan_ssim_combine(const float* sums, float inv_size, int NC, float out_scale, float* val, float grad_scale,
+                       float* coef, void* stream);
+
+/* ---- optimiser (torch.optim.Adam, pix2pix_model.py:122-125) over flat fp32 buffers ---------- */
+/* p,g,m,v: flat fp32 [n]; step_t >= 1.  grad_scale multiplies g first (1/world_size after a sum all-reduce).
+ * p_bf16 (may be NULL) receives the bf16 copy of the updated parameters. */
+int dsgan_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, int step_t, float grad_scale, void* p_bf16, void* stream);
+/* dst bf16 [cols,rows] = transpose(src fp32 [rows,cols]) — packed operand for input-gradient GEMMs. */
+int dsgan_pack_transpose_bf16(const float* src, void* dst, int rows, int cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSGAN_B200_H */

@@ -1,0 +1,224 @@
+"""GPU parity of the network graphs and of one full optimize_parameters() against the oracle (and, at 256x256,
+against the fixture produced by the reference itself)."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import dsgan_oracle as O  # noqa: E402
+from gpu_util import TOL, ctx_for, make_params, q, rel, set_grad, to_var, var_data, var_grad  # noqa: E402
+from dsgan_b200 import nets  # noqa: E402
+from dsgan_b200.models import create_model  # noqa: E402
+from dsgan_b200.options.train_options import TrainOptions  # noqa: E402
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _grads_vs(P, ref_grads, tol, floor=2e-3):
+    gmax = max(float(g.norm()) for g in ref_grads.values())
+    bad = {}
+    for k, g in ref_grads.items():
+        if float(g.norm()) <= floor * gmax:   # mathematically-zero gradients (bias before InstanceNorm): noise
+            continue
+        r = rel(P[k].grad.cpu().reshape(g.shape), g)
+        if r > tol:
+            bad[k] = r
+    return bad
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_convnext_block(prec):
+    ctx = ctx_for(prec)
+    PG = {k: v for k, v in O.init_params_G(3, 0.05).items() if k.startswith("c2.")}
+    x = q(torch.randn(2, 64, 16, 16, generator=_g(1)), prec)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in PG.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = O._block(Pr, "c2", xr)
+    dy = q(torch.randn(yr.shape, generator=_g(2)), prec)
+    yr.backward(dy)
+    P = make_params(PG)
+    xv = to_var(ctx, x)
+    yv = nets._block(ctx, P, "c2", xv)
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    tol = TOL[prec] * 2
+    assert rel(var_data(yv), yr.detach()) < tol
+    assert rel(var_grad(xv), xr.grad) < tol
+    assert not _grads_vs(P, {k: v.grad for k, v in Pr.items()}, tol * 1.5)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_midmlka_and_upsample_and_downskip(prec):
+    ctx = ctx_for(prec)
+    PGall = O.init_params_G(4, 0.05)
+    tol = TOL[prec] * 3
+    # MidMLKA(64)
+    PG = {k: v for k, v in PGall.items() if k.startswith("local.mid64.")}
+    x = q(torch.randn(2, 64, 12, 12, generator=_g(1)), prec)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in PG.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = O._midmlka(Pr, "local.mid64", xr)
+    dy = q(torch.randn(yr.shape, generator=_g(2)), prec)
+    yr.backward(dy)
+    P = make_params(PG)
+    xv = to_var(ctx, x)
+    yv = nets._midmlka(ctx, P, "local.mid64", xv)
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    assert rel(var_data(yv), yr.detach()) < tol
+    assert rel(var_grad(xv), xr.grad) < tol
+    assert not _grads_vs(P, {k: v.grad for k, v in Pr.items()}, tol * 1.5)
+    # upSample(256,128) + cat
+    PG = {k: v for k, v in PGall.items() if k.startswith("u3.")}
+    x, s = q(torch.randn(2, 256, 4, 4, generator=_g(3)), prec), q(torch.randn(2, 128, 8, 8, generator=_g(4)), prec)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in PG.items()}
+    xr, sr = x.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    yr = O._upsample(Pr, "u3", xr, sr)
+    dy = q(torch.randn(yr.shape, generator=_g(5)), prec)
+    yr.backward(dy)
+    P = make_params(PG)
+    xv, sv = to_var(ctx, x), to_var(ctx, s)
+    yv = nets._upsample(ctx, P, "u3.model.0", xv, sv)
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    assert rel(var_data(yv), yr.detach()) < tol
+    assert rel(var_grad(xv), xr.grad) < tol and rel(var_grad(sv), sr.grad) < 1e-6
+    assert not _grads_vs(P, {k: v.grad for k, v in Pr.items()}, tol * 1.5)
+    # downSkip 64 -> 256, pool 4
+    PG = {k: v for k, v in PGall.items() if k.startswith("down64.to4.")}
+    x = q(torch.randn(2, 64, 16, 16, generator=_g(6)), prec)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in PG.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = O._downskip(Pr, "down64.to4", xr, 4)
+    dy = q(torch.randn(yr.shape, generator=_g(7)), prec)
+    yr.backward(dy)
+    P = make_params(PG)
+    xv = to_var(ctx, x)
+    yv = nets._downskip(ctx, P, "down64.to4", xv, 4)
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    assert rel(var_data(yv), yr.detach()) < tol
+    assert rel(var_grad(xv), xr.grad) < tol
+    assert not _grads_vs(P, {k: v.grad for k, v in Pr.items()}, tol * 1.5)
+
+
+@pytest.mark.parametrize("prec,n,hw", [("fp32", 2, 32), ("fp32", 1, 64), ("bf16", 2, 64)])
+def test_generator_forward_backward(prec, n, hw):
+    ctx = ctx_for(prec)
+    PG = O.init_params_G(20, 0.05)
+    A, _ = O.synthetic_pair(n, hw, hw, seed=5)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in PG.items()}
+    yr = O.g_forward(Pr, A)
+    dy = q(torch.randn(yr.shape, generator=_g(2)), prec)
+    yr.backward(dy)
+    P = make_params(PG)
+    yv = nets.generator_forward(ctx, P, to_var(ctx, A))
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    assert rel(var_data(yv), yr.detach()) < (1e-4 if prec == "fp32" else 2e-2)
+    bad = _grads_vs(P, {k: v.grad for k, v in Pr.items()}, 1e-3 if prec == "fp32" else 3e-2)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_discriminator_and_vgg(prec):
+    ctx = ctx_for(prec)
+    PD, PV = O.init_params_D(20, 0.05), O.init_params_vgg(20, 0.05)
+    x = q(torch.randn(2, 6, 64, 64, generator=_g(1)), prec)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in PD.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = O.d_forward(Pr, xr)
+    dy = q(torch.randn(yr.shape, generator=_g(2)), prec)
+    yr.backward(dy)
+    P = make_params(PD)
+    xv = to_var(ctx, x)
+    yv = nets.discriminator_forward(ctx, P, xv)
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    tol = 2e-4 if prec == "fp32" else 3e-2
+    assert rel(var_data(yv), yr.detach()) < tol
+    assert rel(var_grad(xv), xr.grad) < tol
+    assert not _grads_vs(P, {k: v.grad for k, v in Pr.items()}, tol)
+    # VGG taps + input gradient through the four L1 terms
+    img = q(torch.randn(1, 3, 32, 32, generator=_g(3)), prec)
+    ir = img.clone().requires_grad_(True)
+    taps_r = O.vgg_forward(PV, ir)
+    dts = [q(torch.randn(t.shape, generator=_g(10 + i)), prec) * (t.detach() > 0) for i, t in enumerate(taps_r)]
+    torch.autograd.backward(taps_r, dts)
+    P = make_params(PV)
+    ctx.param_grads = False
+    iv = to_var(ctx, img)
+    taps = nets.vgg_forward(ctx, P, iv)
+    for t, d in zip(taps, dts):
+        set_grad(ctx, t, d)
+    ctx.backward()
+    ctx.param_grads = True
+    for t, tr in zip(taps, taps_r):
+        assert rel(var_data(t), tr.detach()) < tol
+    assert rel(var_grad(iv), ir.grad) < tol
+
+
+def _make_model(prec):
+    opt = TrainOptions().parse("/tmp/none", "/tmp/dsgan_b200_test", argv=["--precision", prec], quiet=True)
+    model = create_model(opt)
+    model.setup(opt)
+    return model
+
+
+def _load(model, PG, PD, PV):
+    model.netG.load_state_dict(PG)
+    model.netD.load_state_dict(PD)
+    model.vgg.load_state_dict(PV, strict=False)
+
+
+@pytest.mark.parametrize("prec,n,hw,bias", [("fp32", 2, 32, 0.05), ("bf16", 2, 64, 0.05), ("fp32", 1, 256, 0.05)])
+def test_training_step_matches_oracle(prec, n, hw, bias, golden_dir):
+    torch.set_num_threads(os.cpu_count())
+    PG, PD, PV = O.init_params_G(20, bias), O.init_params_D(20, bias), O.init_params_vgg(20, bias)
+    A, B = O.synthetic_pair(n, hw, hw, seed=1)
+    ref = O.train_step(PG, PD, PV, A, B)
+    model = _make_model(prec)
+    _load(model, PG, PD, PV)
+    model.set_input({"A": A, "B": B, "A_paths": [""], "B_paths": [""]})
+    model.optimize_parameters()
+    torch.cuda.synchronize()
+    got = {k: float(getattr(model, "tv_loss" if k == "tv" else "loss_" + k)) for k in ref["losses"]}
+    ltol = 1e-4 if prec == "fp32" else 1e-3
+    for k, want in ref["losses"].items():
+        assert abs(got[k] - want) <= ltol * max(1.0, abs(want)), (k, got[k], want)
+    assert rel(model.fake_B.cpu(), ref["fake_B"]) < (1e-4 if prec == "fp32" else 2e-2)
+    gtol = 2e-3 if prec == "fp32" else 3e-2
+    PDm, PGm = model.netD.flat_buffers()[2], model.netG.flat_buffers()[2]
+    bad = _grads_vs(PDm, ref["grads_D"], gtol)
+    assert not bad, ("D grads", bad)
+    bad = _grads_vs(PGm, ref["grads_G"], gtol)
+    assert not bad, ("G grads", bad)
+    # Adam: parameters after the step (tensors with real gradients only; lr*sign(noise) otherwise)
+    gmax = max(float(g.norm()) for g in ref["grads_G"].values())
+    for k, g in ref["grads_G"].items():
+        if prec == "fp32" and float(g.norm()) > 2e-3 * gmax:
+            assert rel(PGm[k].data.cpu().reshape(g.shape), ref["PG"][k]) < 1e-3, k
+    if hw == 256 and n == 1:  # the reference's own numbers for this exact configuration
+        rec = [r for r in json.load(open(os.path.join(golden_dir, "train_step.json"))) if r["hw"] == 256][0]
+        for k, want in rec["losses"].items():
+            assert abs(got[k] - want) <= 2e-4 * max(1.0, abs(want)), ("golden", k, got[k], want)
+        fp = O.fingerprint(model.fake_B.cpu())
+        assert abs(fp[0] - rec["fake_B"][0]) < 1e-3 * rec["fake_B"][0]
+
+
+def test_second_step_runs_and_losses_move():
+    model = _make_model("bf16")
+    A, B = O.synthetic_pair(2, 64, 64, seed=3)
+    model.set_input({"A": A, "B": B, "A_paths": [""], "B_paths": [""]})
+    model.optimize_parameters()
+    l1 = model.get_current_losses()
+    model.optimize_parameters()
+    l2 = model.get_current_losses()
+    assert set(l1) == {"G_GAN", "G_L1", "D_real", "D_fake"}
+    assert all(torch.isfinite(torch.tensor(list(l2.values()))))
+    assert l1 != l2
