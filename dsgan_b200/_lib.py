@@ -65,6 +65,7 @@ class _Lib:
             fn.restype, fn.argtypes = restype, argtypes
         if self.cdll.dsgan_abi_version() != 1:
             raise DsganError("ABI version mismatch")
+        self.profiler = None  # optional engine.Profile: CUDA events around every ABI call
 
     def last_error(self):
         return self.cdll.dsgan_last_error().decode()
@@ -76,8 +77,13 @@ class _Lib:
             return fn
 
         def call(*args):
+            prof = self.profiler
+            if prof is not None:
+                tok = prof.begin(short)
             if fn(*args) != 0:
                 raise DsganError("dsgan_%s: %s" % (short, self.last_error()))
+            if prof is not None:
+                prof.end(tok)
         call.__name__ = short
         setattr(self, short, call)
         return call

@@ -78,6 +78,49 @@ class Param:
         return self.grad.data_ptr()
 
 
+FAMILY = {"conv_fwd": "dense", "conv_wgrad": "dense", "tc_gemm": "dense", "tc_wgrad": "dense", "tc_conv": "dense",
+          "colsum": "reduce", "dwconv_fwd": "dwconv", "dwconv_wgrad": "dwconv",
+          "inorm_stats": "norm", "inorm_apply": "norm", "inorm_bwd_stats": "norm", "inorm_bwd_apply": "norm",
+          "maxpool_fwd": "pool", "maxpool_bwd": "pool", "ca_fwd": "ca", "ca_bwd": "ca", "scale_nc_fwd": "ca",
+          "scale_nc_bwd_reduce": "ca", "scale_nc_bwd_apply": "ca",
+          "gan_loss": "loss", "l1_loss": "loss", "tv_loss": "loss", "ssim_fwd": "ssim", "ssim_bwd": "ssim",
+          "avgpool2_fwd": "ssim", "avgpool2_bwd": "ssim", "msssim_combine": "ssim", "ssim_combine": "ssim",
+          "adam_step": "optim", "pack_transpose_bf16": "optim", "pack_bf16": "optim"}
+
+
+class Profile:
+    """CUDA-event timing of every ABI call on the launching stream, grouped into kernel families; the dense
+    (conv / GEMM) family also carries its algorithmic FLOPs (2 x true MACs) for the roofline in bench.py."""
+
+    def __init__(self):
+        self.items = []
+        self.pending_flops = 0.0
+
+    def begin(self, name):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fl, self.pending_flops = self.pending_flops, 0.0
+        return (name, fl, e0)
+
+    def end(self, tok):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.items.append(tok + (e1,))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, fl, e0, e1 in self.items:
+            fam = FAMILY.get(name, "elementwise")
+            d = out.setdefault(fam, {"ms": 0.0, "n": 0, "flops": 0.0, "name": fam})
+            d["ms"] += e0.elapsed_time(e1)
+            d["n"] += 1
+            d["flops"] += fl
+        out.setdefault("dense", {"ms": 0.0, "n": 0, "flops": 0.0, "name": "dense"})
+        out["dense"]["name"] = "dense conv/GEMM family (conv_fwd + conv_wgrad)"
+        return out
+
+
 class Ctx:
     """One engine context per device: dtype mode, tape, scratch, kernel wrappers."""
 
@@ -92,6 +135,22 @@ class Ctx:
         self.tape = []
         self.param_grads = True   # False while D is frozen in the G step (pix2pix_model.py:214)
         self.no_grad = False
+
+    @property
+    def profile(self):
+        return self.L.profiler
+
+    @profile.setter
+    def profile(self, p):
+        self.L.profiler = p
+
+    def _flops(self, geom, transposed_geom=False):
+        """Algorithmic FLOPs = 2 x true MACs of a conv described by geom (strided-transposed ops count the MACs
+        of the equivalent forward conv: every (small-grid pixel, tap, ci, co) once)."""
+        if self.L.profiler is not None:
+            N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+            small = min(Hi * Wi, Ho * Wo) if s > 1 else Ho * Wo
+            self.L.profiler.pending_flops = 2.0 * N * small * Ci * Co * k * k
 
     # ---- memory ---------------------------------------------------------------------------
     @property
@@ -151,12 +210,14 @@ class Ctx:
         N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
         d = self._desc(N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p, transposed, xin[1], out[1], wst, act, dact, acc,
                        aux[1] if aux else 0, pre[1] if pre else 0)
+        self._flops(geom)
         self.L.conv_fwd(ctypes.byref(d), xin[0], w_ptr, bias_ptr, out[0], pre[0] if pre else None,
                         aux[0] if aux else None, self.stream)
 
     def wgrad_raw(self, geom, xin, dout, dw_ptr, wst):
         N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
         d = self._desc(N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p, False, xin[1], dout[1], wst)
+        self._flops(geom)
         self.L.conv_wgrad(ctypes.byref(d), xin[0], dout[0], dw_ptr, self.stream)
 
     def colsum(self, x, npix, C, out_ptr):

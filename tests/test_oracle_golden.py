@@ -68,7 +68,7 @@ def test_ssim_small_and_identity(golden_dir):
     assert float(O.ms_ssim(Z, Z, 1.0)) == pytest.approx(1.0, abs=1e-5)
 
 
-@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
 def test_train_step_golden(golden_dir, case):
     rec = json.load(open(os.path.join(golden_dir, "train_step.json")))[case]
     torch.set_num_threads(os.cpu_count())
