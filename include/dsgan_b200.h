@@ -93,6 +93,22 @@ int dsgan_conv_wgrad(const dsgan_conv_desc* d, const void* in, const void* dout,
 /* out[c] += sum_p x[p,c]: bias gradients. */
 int dsgan_colsum(const void* x, int dtype, int ld, long long npix, int C, float* out, void* stream);
 
+/* ---- tensor-core (tcgen05 + TMEM + TMA) GEMM family: nn.Linear / 1x1 nn.Conv2d in bf16, fp32 accumulate ------
+ * Operands are bf16; weights are the bf16 shadow copy of the fp32 masters in the reference's own [out,in] layout. */
+/* 1 if the shape/pitches are eligible for dsgan_tc_gemm (mode 0/1) or dsgan_tc_wgrad (mode 2). */
+int dsgan_tc_gemm_supported(int mode, long long M, int N, int K, int lda, int ldb, int ldc);
+/* mode 0 (forward):        C[M,N] = epi(A[M,K] . W[N,K]^T)   W = weight [out=N, in=K]   (MixConvNeXtML.py:218,222-224)
+ * mode 1 (input-gradient): C[M,N] = epi(A[M,K] . W[K,N])     W = the same weight [out=K, in=N], read MN-major
+ * epi: v = acc + bias (+ C) ; v *= dact'(aux) ; pre = v ; C = act(v)   — as dsgan_conv_fwd. */
+int dsgan_tc_gemm(int mode, const void* A, int lda, const void* W, int ldb, long long M, int N, int K, void* C, int ldc,
+                  const float* bias, void* pre, int ld_pre, const void* aux, int ld_aux, int act, int dact,
+                  int accumulate, void* stream);
+/* weight-gradient: dW[Co,Ci] (fp32, pitch ld_dw) += dY[P,Co]^T . X[P,Ci]; split over P, fp32 atomics. */
+int dsgan_tc_wgrad(const void* dY, int ld_dy, const void* X, int ld_x, long long P, int Co, int Ci, float* dW, int ld_dw,
+                   void* stream);
+/* dst (bf16) = src (fp32), n elements: refresh of the packed GEMM operands after an optimizer step. */
+int dsgan_pack_bf16(const float* src, void* dst, long long n, void* stream);
+
 /* ---- depthwise convolution (MixConvNeXtML.py:94-97,220: k = 3,5,7,9, stride 1, pad k/2) ---- */
 /* flip=0: forward (w is [C,1,k,k] fp32, bias may be NULL); flip=1: input-gradient (correlate with the
  * flipped kernel, no bias). */
