@@ -64,10 +64,11 @@ class Var:
 
 class Param:
     """fp32 master parameter + fp32 gradient, both views into per-network flat buffers."""
-    __slots__ = ("name", "data", "grad", "cache")
+    __slots__ = ("name", "data", "grad", "cache", "bf16_ptr")
 
-    def __init__(self, name, data, grad):
+    def __init__(self, name, data, grad, bf16_ptr=0):
         self.name, self.data, self.grad, self.cache = name, data, grad, {}
+        self.bf16_ptr = bf16_ptr  # address of this tensor inside the network's flat bf16 shadow copy (0 = none)
 
     @property
     def ptr(self):
@@ -135,6 +136,7 @@ class Ctx:
         self.tape = []
         self.param_grads = True   # False while D is frozen in the G step (pix2pix_model.py:214)
         self.no_grad = False
+        self.use_tc = True        # bf16 mode: route eligible GEMMs to the tcgen05 kernels
 
     @property
     def profile(self):
@@ -220,6 +222,24 @@ class Ctx:
         self._flops(geom)
         self.L.conv_wgrad(ctypes.byref(d), xin[0], dout[0], dw_ptr, self.stream)
 
+    # ---- tensor-core (tcgen05) pointwise GEMMs: used in bf16 mode whenever the shape is eligible -------------
+    def tc_ok(self, mode, M, N, K, lda, ldb, ldc, *ptrs):
+        if self.dt != BF16 or not self.use_tc or any(p % 16 for p in ptrs if p):
+            return False
+        return bool(self.L.cdll.dsgan_tc_gemm_supported(mode, M, N, K, lda, ldb, ldc))
+
+    def tc_gemm(self, mode, a, w_ptr, ldb, M, N, K, out, bias_ptr=None, pre=None, aux=None, act=0, dact=0, acc=0):
+        assert not (acc and dact and dact != ACT_RELU)
+        if self.L.profiler is not None:
+            self.L.profiler.pending_flops = 2.0 * M * N * K
+        self.L.tc_gemm(mode, a[0], a[1], w_ptr, ldb, M, N, K, out[0], out[1], bias_ptr, pre[0] if pre else None,
+                       pre[1] if pre else 0, aux[0] if aux else None, aux[1] if aux else 0, act, dact, acc, self.stream)
+
+    def tc_wgrad(self, dy, x, P, Co, Ci, dw_ptr):
+        if self.L.profiler is not None:
+            self.L.profiler.pending_flops = 2.0 * P * Co * Ci
+        self.L.tc_wgrad(dy[0], dy[1], x[0], x[1], P, Co, Ci, dw_ptr, Ci, self.stream)
+
     def colsum(self, x, npix, C, out_ptr):
         self.L.colsum(x[0], self.dt, x[1], npix, C, out_ptr, self.stream)
 
@@ -265,8 +285,14 @@ def conv2d(ctx: Ctx, x: Var, w: Param, b, k, stride=1, pad=0, act=ACT_NONE, out:
     pre = None
     if act == ACT_GELU or keep_pre:
         pre = ctx.new(x.N, Ho, Wo, Co)
-    ctx.conv_raw(geom, (x.ptr, x.ld), w.ptr, wst_conv(Co, Ci, k), b.ptr if b is not None else None, (y.ptr, y.ld),
-                 act=act, acc=acc, pre=(pre.ptr, pre.ld) if pre is not None else None)
+    M = x.npix
+    pointwise = k == 1 and stride == 1 and pad == 0 and w.bf16_ptr
+    prep = (pre.ptr, pre.ld) if pre is not None else None
+    bptr = b.ptr if b is not None else None
+    if pointwise and ctx.tc_ok(0, M, Co, Ci, x.ld, Ci, y.ld, x.ptr, y.ptr, w.bf16_ptr, pre.ptr if pre else 0):
+        ctx.tc_gemm(0, (x.ptr, x.ld), w.bf16_ptr, Ci, M, Co, Ci, (y.ptr, y.ld), bptr, prep, None, act, 0, acc)
+    else:
+        ctx.conv_raw(geom, (x.ptr, x.ld), w.ptr, wst_conv(Co, Ci, k), bptr, (y.ptr, y.ld), act=act, acc=acc, pre=prep)
     if act != ACT_NONE:
         y.fused_act = (act, pre if act == ACT_GELU else y)
     train_w = ctx.param_grads
@@ -276,16 +302,19 @@ def conv2d(ctx: Ctx, x: Var, w: Param, b, k, stride=1, pad=0, act=ACT_NONE, out:
         if gi is None:
             return
         if train_w:
-            ctx.wgrad_raw(geom, (x.ptr, x.ld), gi, w.gptr, wst_conv(Co, Ci, k))
+            if pointwise and ctx.tc_ok(2, M, Ci, Co, gi[1], x.ld, Ci, gi[0], x.ptr):
+                ctx.tc_wgrad(gi, (x.ptr, x.ld), M, Co, Ci, w.gptr)
+            else:
+                ctx.wgrad_raw(geom, (x.ptr, x.ld), gi, w.gptr, wst_conv(Co, Ci, k))
             if b is not None:
                 ctx.colsum(gi, y.npix, Co, b.gptr)
         if need_dx:
-            conv2d_dgrad(ctx, x, gi, w, geom)
+            conv2d_dgrad(ctx, x, gi, w, geom, pointwise)
     ctx.record(bwd)
     return y
 
 
-def conv2d_dgrad(ctx, x: Var, gi, w: Param, geom):
+def conv2d_dgrad(ctx, x: Var, gi, w: Param, geom, pointwise=False):
     """dx (=|+=) conv-transpose of the output gradient; applies x.fused_act' in the epilogue."""
     N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
     gp, gld, gacc = x.grad_out()
@@ -293,6 +322,10 @@ def conv2d_dgrad(ctx, x: Var, gi, w: Param, geom):
     if x.fused_act is not None:
         dact, av = x.fused_act
         aux = (av.ptr, av.ld)
+    M = N * Hi * Wi
+    if pointwise and ctx.tc_ok(1, M, Ci, Co, gi[1], Ci, gld, gi[0], gp, w.bf16_ptr, aux[0] if aux else 0):
+        ctx.tc_gemm(1, gi, w.bf16_ptr, Ci, M, Ci, Co, (gp, gld), None, None, aux, 0, dact, gacc)
+        return
     g2 = (N, Ho, Wo, Co, Hi, Wi, Ci, k, s, p)
     ctx.conv_raw(g2, gi, w.ptr, wst_conv_T(Co, Ci, k), None, (gp, gld), dact=dact, acc=gacc, aux=aux, transposed=True)
 

@@ -63,7 +63,12 @@ class KernelNet(nets.ParamTree):
         return get_ctx(dev, self.precision)
 
     def params(self):
-        return self.flat_buffers()[2]
+        """{name: Param}; in bf16 mode the packed bf16 operands are refreshed first."""
+        P = self.flat_buffers()[2]
+        ctx = self.ctx()
+        if ctx.precision == "bf16":
+            self.refresh_bf16(ctx)
+        return P
 
 
 class MixConvNeXtML(KernelNet):

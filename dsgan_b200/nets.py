@@ -39,6 +39,7 @@ class ParamTree(nn.Module):
             off += n
         self._flat = flat
         self._flat_grad = None
+        self._flat_bf16 = None
         self._plist = None
 
     def init_normal(self, gain=0.02):
@@ -77,9 +78,18 @@ class ParamTree(nn.Module):
                 params[name].grad = grad[off:off + n].view(shape)
                 off += n
             self._flat, self._flat_grad, self._plist = flat, grad, None
+            self._flat_bf16 = torch.empty(self._numel, dtype=torch.bfloat16, device=dev)
         if self._plist is None:
-            self._plist = {n: Param(n, p.data, p.grad) for n, p in params.items()}
+            base32, base16 = self._flat.data_ptr(), self._flat_bf16.data_ptr()
+            self._plist = {n: Param(n, p.data, p.grad, base16 + (p.data_ptr() - base32) // 2)
+                           for n, p in params.items()}
         return self._flat, self._flat_grad, self._plist
+
+    def refresh_bf16(self, ctx):
+        """Re-derive the bf16 GEMM operands from the fp32 masters (one pass over the flat buffer).  Called at the
+        start of every forward so load_state_dict / in-place edits / optimizer steps can never leave them stale."""
+        flat, _g, _p = self.flat_buffers()
+        ctx.L.pack_bf16(flat.data_ptr(), self._flat_bf16.data_ptr(), flat.numel(), ctx.stream)
 
 
 # ------------------------------------------------------------------------------------------------

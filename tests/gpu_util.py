@@ -41,7 +41,9 @@ def make_params(tensors):
     out = {}
     for k, t in tensors.items():
         d = t.detach().clone().float().cuda()
-        out[k] = Param(k, d, torch.zeros_like(d))
+        sh = d.bfloat16()
+        out[k] = Param(k, d, torch.zeros_like(d), sh.data_ptr())
+        out[k].cache["bf16"] = sh  # keep the shadow alive
     return out
 
 

@@ -94,7 +94,7 @@ def test_tc_wgrad(P, Co, Ci):
     X = torch.randn(P, Ci, generator=_g(2)).bfloat16()
     ref = dY.float().t() @ X.float()
     dW0 = torch.randn(Co, Ci, generator=_g(3))
-    dW = dW0.cuda()
-    L.tc_wgrad(dY.cuda().data_ptr(), Co, X.cuda().data_ptr(), Ci, P, Co, Ci, dW.data_ptr(), Ci, _stream())
+    dW, dYd, Xd = dW0.cuda(), dY.cuda(), X.cuda()   # keep the device operands alive across the launch
+    L.tc_wgrad(dYd.data_ptr(), Co, Xd.data_ptr(), Ci, P, Co, Ci, dW.data_ptr(), Ci, _stream())
     torch.cuda.synchronize()
     assert _rel(dW.cpu() - dW0, ref) < 2e-3
