@@ -21,6 +21,15 @@ class ConvDesc(ctypes.Structure):
                [(n, ctypes.c_int) for n in ("act", "dact", "accumulate")]
 
 
+class TcConvDesc(ctypes.Structure):
+    """Mirror of dsgan_tc_conv_desc."""
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("N", "Hi", "Wi", "Ci", "ld_in", "Ho", "Wo", "Co", "ld_out", "Hg", "Wg", "in_stride", "out_stride",
+                 "oy0", "ox0", "ntaps", "nslabs")] + \
+               [("dy", ctypes.c_int * 16), ("dx", ctypes.c_int * 16), ("slab", ctypes.c_int * 16)] + \
+               [(n, ctypes.c_int) for n in ("ld_aux", "ld_pre", "act", "dact", "accumulate")]
+
+
 _SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
             "unsigned long long": ctypes.c_ulonglong, "size_t": ctypes.c_size_t, "unsigned": ctypes.c_uint}
 

@@ -1,0 +1,344 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution over NHWC bf16 activations.
+//
+// One output tile = an 8x16 patch of "grid positions" of one image (128 GEMM rows) x BN output channels.  For every
+// filter tap the A operand is ONE 4-D TMA box {64 channels, 16, 8, 1} of the input, fetched at the tap's spatial offset —
+// out-of-image coordinates are zero-filled by TMA, which implements the padding — and the B operand is a K-major slab
+// [tap][Cout][Cin] of the packed bf16 weights.  Grid position (y,x) reads input pixel (y*is + dy_t, x*is + dx_t) and writes
+// output pixel (y*os + oy0, x*os + ox0), which covers
+//   * nn.Conv2d stride 1 (VGG 3x3, PatchGAN 4x4 s1) and its input-gradient (flipped taps, transposed slabs)    is=1 os=1
+//   * nn.Conv2d stride 2 (PatchGAN 4x4 s2) and the input-gradient of nn.ConvTranspose2d(s2)                    is=2 os=1
+//   * nn.ConvTranspose2d(k3,s2,p1,op1) forward and the input-gradient of a stride-2 conv, one launch per output
+//     parity class (1/2/2/4 taps)                                                                              is=1 os=2
+// Reference op sites: models/vgg.py:16-25, networks.py:544-569, MixConvNeXtML.py:53,150.
+// Same warp-specialised persistent pipeline as tc_gemm.cu (TMA warp / single-thread MMA issuer / 4 epilogue warps,
+// 4-stage smem ring, double-buffered TMEM accumulator).
+#include "tc_common.cuh"
+#include "../../include/dsgan_b200.h"
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <string.h>
+
+using namespace dsgan;
+using namespace dsgan::tc;
+
+namespace {
+constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, STAGES = 4, NUM_THREADS = 192, MAX_TAPS = 16;
+
+struct ConvParams {
+  int N, Hg, Wg;            // images, grid extent (positions per image)
+  int Ci, Co;
+  int is_, os_, oy0, ox0;   // input stride, output stride, output parity offset
+  int Ho, Wo;               // output extent (pixels)
+  int ntaps;
+  int dy[MAX_TAPS], dx[MAX_TAPS], slab[MAX_TAPS];
+  int tiles_y, tiles_x, n_tiles;
+  void* C; int ldc;
+  const float* bias;
+  void* pre; int ld_pre;
+  const void* aux; int ld_aux;
+  int act, dact, accumulate;
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using SL = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int num_tiles = p.N * tiles_per_img * p.n_tiles;
+  const int kc = p.Ci / BK;  // channel blocks per tap
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int sp = tile / p.n_tiles;
+        const int img = sp / tiles_per_img, t2 = sp % tiles_per_img;
+        const int y0 = (t2 / p.tiles_x) * TH, x0 = (t2 % p.tiles_x) * TW;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int cy = y0 * p.is_ + p.dy[t], cx = x0 * p.is_ + p.dx[t];
+          for (int c = 0; c < kc; ++c) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * SL::STAGE_BYTES;
+            mbar_expect_tx(&full[stage], SL::STAGE_BYTES);
+            tma_load_4d(sa, &tmA, &full[stage], c * BK, cx, cy, img);
+            tma_load_2d(sa + SL::A_BYTES, &tmB, &full[stage], c * BK, p.slab[t] * p.Co + n_blk * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = idesc_bf16(BM, BN, false, false);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const int nk = p.ntaps * kc;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
+          const uint64_t adesc = smem_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = smem_desc_sw128(sa + SL::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int sp = tile / p.n_tiles;
+      const int img = sp / tiles_per_img, t2 = sp % tiles_per_img;
+      const int r = quarter * 32 + lane;
+      const int gy = (t2 / p.tiles_x) * TH + r / TW, gx = (t2 % p.tiles_x) * TW + r % TW;
+      const int oy = gy * p.os_ + p.oy0, ox = gx * p.os_ + p.ox0;
+      const bool row_ok = gy < p.Hg && gx < p.Wg && oy < p.Ho && ox < p.Wo;
+      const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.Co) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+          }
+          bf16* o = reinterpret_cast<bf16*>(p.C) + pix * p.ldc + col0;
+          if (p.accumulate) {
+            const uint4* op = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = op[q];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                f[q * 8 + e * 2] += __low2float(h);
+                f[q * 8 + e * 2 + 1] += __high2float(h);
+              }
+            }
+          }
+          if (p.dact) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + pix * p.ld_aux + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = __ldg(ap + q);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                f[q * 8 + e * 2] *= act_bwd(p.dact, __low2float(h));
+                f[q * 8 + e * 2 + 1] *= act_bwd(p.dact, __high2float(h));
+              }
+            }
+          }
+          if (p.pre) {
+            uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.pre) + pix * p.ld_pre + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              pp[q] = make_uint4(pack2(f[q * 8], f[q * 8 + 1]), pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                                 pack2(f[q * 8 + 4], f[q * 8 + 5]), pack2(f[q * 8 + 6], f[q * 8 + 7]));
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = act_fwd(p.act, f[j]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            op[q] = make_uint4(pack2(f[q * 8], f[q * 8 + 1]), pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                               pack2(f[q * 8 + 4], f[q * 8 + 5]), pack2(f[q * 8 + 6], f[q * 8 + 7]));
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------
+struct Key4 {
+  const void* base; uint64_t c, w, h, n, ld; uint32_t es;
+  bool operator<(const Key4& o) const {
+    return std::tie(base, c, w, h, n, ld, es) < std::tie(o.base, o.c, o.w, o.h, o.n, o.ld, o.es);
+  }
+};
+std::map<Key4, CUtensorMap> g_maps4;
+struct Key2 {
+  const void* base; uint64_t d0, d1; uint32_t b1;
+  bool operator<(const Key2& o) const { return std::tie(base, d0, d1, b1) < std::tie(o.base, o.d0, o.d1, o.b1); }
+};
+std::map<Key2, CUtensorMap> g_maps2;
+std::mutex g_mu;
+
+int map_input(CUtensorMap* out, const void* base, int N, int H, int W, int C, int ld, int es) {
+  Key4 k{base, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)ld, (uint32_t)es};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps4.find(k);
+  if (it != g_maps4.end()) { *out = it->second; return 0; }
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  uint32_t box[4] = {64, (uint32_t)(TW * es), (uint32_t)(TH * es), 1};
+  uint32_t estr[4] = {1, (uint32_t)es, (uint32_t)es, 1};
+  if (encode_tmap_bf16(out, base, 4, dims, strides, box, estr)) return 1;
+  if (g_maps4.size() > 4096) g_maps4.clear();
+  g_maps4[k] = *out;
+  return 0;
+}
+int map_weight(CUtensorMap* out, const void* base, int Ci, int rows, int bn) {
+  Key2 k{base, (uint64_t)Ci, (uint64_t)rows, (uint32_t)bn};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps2.find(k);
+  if (it != g_maps2.end()) { *out = it->second; return 0; }
+  uint64_t dims[2] = {(uint64_t)Ci, (uint64_t)rows}, strides[1] = {(uint64_t)Ci * 2};
+  uint32_t box[2] = {64, (uint32_t)bn};
+  if (encode_tmap_bf16(out, base, 2, dims, strides, box, nullptr)) return 1;
+  if (g_maps2.size() > 4096) g_maps2.clear();
+  g_maps2[k] = *out;
+  return 0;
+}
+
+int g_sms = 0;
+int sms() {
+  if (!g_sms) { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, d); }
+  return g_sms;
+}
+
+template <int BN>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
+  static bool attr = false;
+  constexpr int smem = SmemLayout<BN>::TOTAL;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("tc_conv smem attr: %s", cudaGetErrorString(e)); return 1; }
+    attr = true;
+  }
+  const long long tiles = (long long)p.N * p.tiles_y * p.tiles_x * p.n_tiles;
+  const int grid = tiles < sms() ? (int)tiles : sms();
+  k_tc_conv<BN><<<grid, NUM_THREADS, smem, s>>>(a, b, p);
+  return DS_LAUNCHED("tc_conv");
+}
+
+// dst[slab][o][i] (bf16) = src[o*so + i*si + tap_offset(slab)]  — packs OIHW / IOHW fp32 weights into K-major slabs
+__global__ void k_pack_slabs(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int kh, int kw,
+                             long long so, long long si, long long sky, long long skx, int flip) {
+  const long long total = (long long)kh * kw * O * I;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx % I);
+    const int o = (int)((idx / I) % O);
+    const int slab = (int)(idx / ((long long)I * O));
+    int ky = slab / kw, kx = slab % kw;
+    if (flip) { ky = kh - 1 - ky; kx = kw - 1 - kx; }
+    dst[idx] = __float2bfloat16_rn(src[o * so + i * si + ky * sky + kx * skx]);
+  }
+}
+}  // namespace
+
+extern "C" {
+int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int kh, int kw, long long s_o, long long s_i,
+                           long long s_ky, long long s_kx, int flip, void* stream) {
+  const long long total = (long long)kh * kw * O * I;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_pack_slabs<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, O, I, kh, kw, s_o, s_i, s_ky, s_kx, flip);
+  return DS_LAUNCHED("pack_conv_weight");
+}
+
+int dsgan_tc_conv_supported(int Ci, int Co, int ld_in, int ld_out) {
+  return (Ci % 64 == 0) && (Co % 32 == 0) && Co >= 32 && (ld_in % 8 == 0) && (ld_out % 8 == 0);
+}
+
+int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, const float* bias, void* out,
+                  void* pre_out, const void* aux, void* stream) {
+  DS_REQUIRE(d && in && w_slabs && out, "tc_conv: null argument");
+  DS_REQUIRE(dsgan_tc_conv_supported(d->Ci, d->Co, d->ld_in, d->ld_out), "tc_conv: unsupported Ci=%d Co=%d", d->Ci, d->Co);
+  DS_REQUIRE(d->ntaps >= 1 && d->ntaps <= MAX_TAPS, "tc_conv: ntaps=%d", d->ntaps);
+  DS_REQUIRE(d->in_stride == 1 || d->in_stride == 2, "tc_conv: in_stride=%d", d->in_stride);
+  DS_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)w_slabs % 16 == 0) && ((uintptr_t)out % 16 == 0), "tc_conv: unaligned");
+  DS_REQUIRE(!d->dact || aux, "tc_conv: dact needs aux");
+  const int BN = d->Co >= 256 ? 256 : (d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32));
+  CUtensorMap ta, tb;
+  if (map_input(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in, d->in_stride)) return 1;
+  if (map_weight(&tb, w_slabs, d->Ci, d->nslabs * d->Co, BN)) return 1;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Ci = d->Ci; p.Co = d->Co;
+  p.is_ = d->in_stride; p.os_ = d->out_stride; p.oy0 = d->oy0; p.ox0 = d->ox0; p.Ho = d->Ho; p.Wo = d->Wo;
+  p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.slab[t] = d->slab[t]; }
+  p.tiles_y = (d->Hg + TH - 1) / TH; p.tiles_x = (d->Wg + TW - 1) / TW; p.n_tiles = (d->Co + BN - 1) / BN;
+  p.C = out; p.ldc = d->ld_out; p.bias = bias; p.pre = pre_out; p.ld_pre = d->ld_pre; p.aux = aux; p.ld_aux = d->ld_aux;
+  p.act = d->act; p.dact = d->dact; p.accumulate = d->accumulate;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (BN == 256) return launch<256>(ta, tb, p, s);
+  if (BN == 128) return launch<128>(ta, tb, p, s);
+  if (BN == 64) return launch<64>(ta, tb, p, s);
+  return launch<32>(ta, tb, p, s);
+}
+}

@@ -12,7 +12,7 @@ import ctypes
 
 import torch
 
-from ._lib import ConvDesc, lib, require_device
+from ._lib import ConvDesc, TcConvDesc, lib, require_device
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -137,6 +137,7 @@ class Ctx:
         self.param_grads = True   # False while D is frozen in the G step (pix2pix_model.py:214)
         self.no_grad = False
         self.use_tc = True        # bf16 mode: route eligible GEMMs to the tcgen05 kernels
+        self.pack_epoch = 0       # bumped whenever a network's fp32 masters may have changed (ParamTree.refresh_bf16)
 
     @property
     def profile(self):
@@ -205,11 +206,63 @@ class Ctx:
         d.act, d.dact, d.accumulate = act, dact, acc
         return d
 
-    def conv_raw(self, geom, xin, w_ptr, wst, bias_ptr, out, act=0, dact=0, acc=0, aux=None, pre=None,
+    def _slabs(self, w, O, I, k, wst):
+        """bf16 [k*k][O][I] K-major slabs of a conv weight for the tcgen05 implicit GEMM, cached per pack epoch."""
+        key = ("slabs", O, I, wst)
+        hit = w.cache.get(key)
+        if hit is None or hit[0] != self.pack_epoch:
+            buf = hit[1] if hit is not None else torch.empty(k * k * O * I, dtype=torch.bfloat16, device=self.device)
+            self.L.pack_conv_weight(w.ptr, buf.data_ptr(), O, I, k, k, wst[0], wst[1], wst[2], wst[3], 0, self.stream)
+            w.cache[key] = hit = (self.pack_epoch, buf)
+        return hit[1].data_ptr()
+
+    def _tc_conv(self, geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):
+        """tcgen05 implicit-GEMM path of conv_raw; returns False when the shape is not eligible."""
+        N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+        if self.dt != BF16 or not self.use_tc or k * k > 16 or s not in (1, 2) or not hasattr(w, "cache"):
+            return False
+        if not self.L.cdll.dsgan_tc_conv_supported(Ci, Co, xin[1], out[1]):
+            return False
+        ptrs = [xin[0], out[0]] + ([aux[0]] if aux else []) + ([pre[0]] if pre else [])
+        if any(q % 16 for q in ptrs) or (aux and aux[1] % 8) or (pre and pre[1] % 8):
+            return False
+        slabs = self._slabs(w, Co, Ci, k, wst)
+        d = TcConvDesc()
+        d.N, d.Hi, d.Wi, d.Ci, d.ld_in = N, Hi, Wi, Ci, xin[1]
+        d.Ho, d.Wo, d.Co, d.ld_out = Ho, Wo, Co, out[1]
+        d.nslabs = k * k
+        d.ld_aux, d.ld_pre = (aux[1] if aux else 0), (pre[1] if pre else 0)
+        d.act, d.dact, d.accumulate = act, dact, acc
+        self._flops(geom)
+        launches = []
+        if not transposed:      # out[o] = sum_k in[o*s - p + k]
+            launches.append((Ho, Wo, s, 1, 0, 0, [(ky - p, kx - p, ky * k + kx) for ky in range(k) for kx in range(k)]))
+        elif s == 1:            # out[o] = sum_k in[o + p - k]
+            launches.append((Ho, Wo, 1, 1, 0, 0, [(p - ky, p - kx, ky * k + kx) for ky in range(k) for kx in range(k)]))
+        else:                   # out[o] = sum_k in[(o + p - k)/2]: one launch per output parity class
+            for py in range(2):
+                for px in range(2):
+                    taps = [((py + p - ky) // 2, (px + p - kx) // 2, ky * k + kx) for ky in range(k) for kx in range(k)
+                            if (py + p - ky) % 2 == 0 and (px + p - kx) % 2 == 0]
+                    launches.append(((Ho - py + 1) // 2, (Wo - px + 1) // 2, 1, 2, py, px, taps))
+        for Hg, Wg, is_, os_, oy0, ox0, taps in launches:
+            if not taps or Hg <= 0 or Wg <= 0:
+                continue
+            d.Hg, d.Wg, d.in_stride, d.out_stride, d.oy0, d.ox0, d.ntaps = Hg, Wg, is_, os_, oy0, ox0, len(taps)
+            for i, (dy, dx, sl) in enumerate(taps):
+                d.dy[i], d.dx[i], d.slab[i] = dy, dx, sl
+            self.L.tc_conv(ctypes.byref(d), xin[0], slabs, bias_ptr, out[0], pre[0] if pre else None,
+                           aux[0] if aux else None, self.stream)
+        return True
+
+    def conv_raw(self, geom, xin, w, wst, bias_ptr, out, act=0, dact=0, acc=0, aux=None, pre=None,
                  transposed=False):
-        """geom = (N,Hi,Wi,Ci,Ho,Wo,Co,k,stride,pad); xin/out/aux/pre = (ptr, ld)."""
+        """geom = (N,Hi,Wi,Ci,Ho,Wo,Co,k,stride,pad); xin/out/aux/pre = (ptr, ld); w = Param (or raw fp32 pointer)."""
         assert not (acc and dact and dact != ACT_RELU), "accumulate+dact is only exact for the idempotent ReLU mask"
         N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+        if k > 1 and self._tc_conv(geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):
+            return
+        w_ptr = w.ptr if hasattr(w, "ptr") else w
         d = self._desc(N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p, transposed, xin[1], out[1], wst, act, dact, acc,
                        aux[1] if aux else 0, pre[1] if pre else 0)
         self._flops(geom)
@@ -292,7 +345,7 @@ def conv2d(ctx: Ctx, x: Var, w: Param, b, k, stride=1, pad=0, act=ACT_NONE, out:
     if pointwise and ctx.tc_ok(0, M, Co, Ci, x.ld, Ci, y.ld, x.ptr, y.ptr, w.bf16_ptr, pre.ptr if pre else 0):
         ctx.tc_gemm(0, (x.ptr, x.ld), w.bf16_ptr, Ci, M, Co, Ci, (y.ptr, y.ld), bptr, prep, None, act, 0, acc)
     else:
-        ctx.conv_raw(geom, (x.ptr, x.ld), w.ptr, wst_conv(Co, Ci, k), bptr, (y.ptr, y.ld), act=act, acc=acc, pre=prep)
+        ctx.conv_raw(geom, (x.ptr, x.ld), w, wst_conv(Co, Ci, k), bptr, (y.ptr, y.ld), act=act, acc=acc, pre=prep)
     if act != ACT_NONE:
         y.fused_act = (act, pre if act == ACT_GELU else y)
     train_w = ctx.param_grads
@@ -327,7 +380,7 @@ def conv2d_dgrad(ctx, x: Var, gi, w: Param, geom, pointwise=False):
         ctx.tc_gemm(1, gi, w.bf16_ptr, Ci, M, Ci, Co, (gp, gld), None, None, aux, 0, dact, gacc)
         return
     g2 = (N, Ho, Wo, Co, Hi, Wi, Ci, k, s, p)
-    ctx.conv_raw(g2, gi, w.ptr, wst_conv_T(Co, Ci, k), None, (gp, gld), dact=dact, acc=gacc, aux=aux, transposed=True)
+    ctx.conv_raw(g2, gi, w, wst_conv_T(Co, Ci, k), None, (gp, gld), dact=dact, acc=gacc, aux=aux, transposed=True)
 
 
 def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
@@ -337,7 +390,7 @@ def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
     Ho, Wo = 2 * x.H, 2 * x.W
     y = ctx.new(x.N, Ho, Wo, Co)
     gf = (x.N, x.H, x.W, Ci, Ho, Wo, Co, k, 2, 1)
-    ctx.conv_raw(gf, (x.ptr, x.ld), w.ptr, wst_convT(Ci, Co, k), b.ptr, (y.ptr, y.ld), transposed=True)
+    ctx.conv_raw(gf, (x.ptr, x.ld), w, wst_convT(Ci, Co, k), b.ptr, (y.ptr, y.ld), transposed=True)
     train_w = ctx.param_grads
 
     def bwd():
@@ -351,7 +404,7 @@ def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
             ctx.colsum(gi, y.npix, Co, b.gptr)
         gp, gld, gacc = x.grad_out()
         assert x.fused_act is None
-        ctx.conv_raw(gb, gi, w.ptr, wst_convT_T(Ci, Co, k), None, (gp, gld), acc=gacc)
+        ctx.conv_raw(gb, gi, w, wst_convT_T(Ci, Co, k), None, (gp, gld), acc=gacc)
     ctx.record(bwd)
     return y
 

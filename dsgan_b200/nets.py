@@ -90,6 +90,7 @@ class ParamTree(nn.Module):
         start of every forward so load_state_dict / in-place edits / optimizer steps can never leave them stale."""
         flat, _g, _p = self.flat_buffers()
         ctx.L.pack_bf16(flat.data_ptr(), self._flat_bf16.data_ptr(), flat.numel(), ctx.stream)
+        ctx.pack_epoch += 1  # conv-weight slabs cached on the Params are re-packed lazily
 
 
 # ------------------------------------------------------------------------------------------------

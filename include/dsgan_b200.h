@@ -109,6 +109,27 @@ int dsgan_tc_wgrad(const void* dY, int ld_dy, const void* X, int ld_x, long long
 /* dst (bf16) = src (fp32), n elements: refresh of the packed GEMM operands after an optimizer step. */
 int dsgan_pack_bf16(const float* src, void* dst, long long n, void* stream);
 
+/* tensor-core implicit-GEMM convolution (csrc/tc_conv.cu).  Grid position (y,x) of image n reads input pixel
+ * (y*in_stride + dy[t], x*in_stride + dx[t]) for tap t (zero outside the image) against weight slab slab[t], and writes
+ * output pixel (y*out_stride + oy0, x*out_stride + ox0).  w_slabs: bf16 [nslabs][Co][Ci] (dsgan_pack_conv_weight).
+ * Covers nn.Conv2d s1/s2 and nn.ConvTranspose2d(s2) forward and input-gradients: models/vgg.py:16-25,
+ * networks.py:544-569, MixConvNeXtML.py:53,150.  Epilogue as dsgan_conv_fwd. */
+typedef struct {
+  int N, Hi, Wi, Ci, ld_in;
+  int Ho, Wo, Co, ld_out;
+  int Hg, Wg;
+  int in_stride, out_stride, oy0, ox0;
+  int ntaps, nslabs;
+  int dy[16], dx[16], slab[16];
+  int ld_aux, ld_pre, act, dact, accumulate;
+} dsgan_tc_conv_desc;
+int dsgan_tc_conv_supported(int Ci, int Co, int ld_in, int ld_out);
+int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, const float* bias, void* out,
+                  void* pre_out, const void* aux, void* stream);
+/* dst[slab=ky*kw+kx][o][i] (bf16) = src[o*s_o + i*s_i + ky'*s_ky + kx'*s_kx], (ky',kx') = flipped tap if flip. */
+int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int kh, int kw, long long s_o, long long s_i,
+                           long long s_ky, long long s_kx, int flip, void* stream);
+
 /* ---- depthwise convolution (MixConvNeXtML.py:94-97,220: k = 3,5,7,9, stride 1, pad k/2) ---- */
 /* flip=0: forward (w is [C,1,k,k] fp32, bias may be NULL); flip=1: input-gradient (correlate with the
  * flipped kernel, no bias). */

@@ -22,6 +22,10 @@ def _g(seed):
     (2, 3, 16, 16, 12, 1, 1, 0, "gelu"), (2, 64, 8, 8, 256, 1, 1, 0, "gelu"), (1, 70, 9, 7, 33, 1, 1, 0, None),
     (2, 6, 32, 32, 32, 4, 2, 1, "leaky"), (2, 32, 16, 16, 64, 4, 2, 1, None), (1, 16, 9, 9, 8, 4, 1, 1, None),
     (2, 64, 8, 8, 3, 3, 1, 1, None), (1, 3, 16, 16, 64, 3, 1, 1, "relu"), (1, 256, 5, 5, 1, 4, 1, 1, None),
+    # shapes eligible for the tcgen05 implicit GEMM in bf16 mode (Ci % 64 == 0, Co % 32 == 0)
+    (2, 64, 16, 16, 64, 3, 1, 1, "relu"), (1, 128, 32, 32, 256, 3, 1, 1, None), (1, 64, 9, 13, 96, 3, 1, 1, "relu"),
+    (2, 64, 32, 32, 128, 4, 2, 1, None), (1, 128, 32, 32, 256, 4, 1, 1, None), (1, 64, 18, 10, 32, 4, 2, 1, "leaky"),
+    (1, 512, 8, 8, 512, 3, 1, 1, "relu"),
 ])
 def test_conv2d(prec, cfg):
     N, Ci, H, W, Co, k, s, p, act = cfg
@@ -77,7 +81,8 @@ def test_conv_dgrad_fused_act_chain(prec):
 
 
 @pytest.mark.parametrize("prec", PREC)
-@pytest.mark.parametrize("cfg", [(2, 16, 4, 4, 8), (1, 128, 8, 8, 64), (2, 5, 3, 6, 7)])
+@pytest.mark.parametrize("cfg", [(2, 16, 4, 4, 8), (1, 128, 8, 8, 64), (2, 5, 3, 6, 7), (2, 256, 16, 16, 128),
+                                 (1, 128, 5, 9, 64), (1, 1024, 4, 4, 512)])
 def test_conv_transpose2d(prec, cfg):
     N, Ci, H, W, Co = cfg
     ctx = ctx_for(prec)

@@ -179,7 +179,10 @@ def test_discriminator_and_vgg(prec):
             ya = O.d_forward(Pa, xa)
         ya.backward(dy.to(ya.dtype))
         assert rel(var_grad(xv), xr.grad) < 1.5 * rel(xa.grad, xr.grad) + 1e-2
-    assert not _grads_vs(P, {k: v.grad for k, v in Pr.items()}, tol)
+        for k, v in Pr.items():
+            assert rel(P[k].grad.cpu().reshape(v.shape), v.grad) < 1.5 * rel(Pa[k].grad, v.grad) + 1e-2, k
+    if prec == "fp32":
+        assert not _grads_vs(P, {k: v.grad for k, v in Pr.items()}, tol)
     # VGG taps + input gradient through the four L1 terms
     img = q(torch.randn(1, 3, 32, 32, generator=_g(3)), prec)
     ir = img.clone().requires_grad_(True)
