@@ -193,6 +193,9 @@ def run_ours(args):
     model.optimize_parameters()
     torch.cuda.synchronize()
     prof = ctx.profile.summary()
+    if rank == 0 and args.detail:
+        for ms_, n_, tf_, name_ in ctx.profile.detail(40):
+            print("%9.3f ms  x%-4d %8.1f TF/s  %s" % (ms_, n_, tf_, name_), file=sys.stderr)
     ctx.profile = None
 
     if rank != 0:
@@ -238,6 +241,7 @@ def main():
     ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=2, help="images per CPU reference step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="print the per-kernel profile to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -96,12 +96,26 @@ class Profile:
     def __init__(self):
         self.items = []
         self.pending_flops = 0.0
+        self.label = ""
 
     def begin(self, name):
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
         fl, self.pending_flops = self.pending_flops, 0.0
-        return (name, fl, e0)
+        return (name + (" " + self.label if FAMILY.get(name) == "dense" else ""), fl, e0)
+
+    def detail(self, top=25):
+        """[(ms, launches, TFLOP/s, 'abi-name label')] sorted by time."""
+        torch.cuda.synchronize()
+        agg = {}
+        for name, fl, e0, e1 in self.items:
+            d = agg.setdefault(name, [0.0, 0, 0.0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+            d[2] += fl
+        rows = sorted(((v[0], v[1], (v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), k) for k, v in agg.items()),
+                      reverse=True)
+        return rows[:top]
 
     def end(self, tok):
         e1 = torch.cuda.Event(enable_timing=True)
@@ -112,7 +126,7 @@ class Profile:
         torch.cuda.synchronize()
         out = {}
         for name, fl, e0, e1 in self.items:
-            fam = FAMILY.get(name, "elementwise")
+            fam = FAMILY.get(name.split(" ")[0], "elementwise")
             d = out.setdefault(fam, {"ms": 0.0, "n": 0, "flops": 0.0, "name": fam})
             d["ms"] += e0.elapsed_time(e1)
             d["n"] += 1
@@ -154,6 +168,7 @@ class Ctx:
             N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
             small = min(Hi * Wi, Ho * Wo) if s > 1 else Ho * Wo
             self.L.profiler.pending_flops = 2.0 * N * small * Ci * Co * k * k
+            self.L.profiler.label = "k%ds%d %d->%d @%dx%d->%dx%d" % (k, s, Ci, Co, Hi, Wi, Ho, Wo)
 
     # ---- memory ---------------------------------------------------------------------------
     @property
@@ -285,12 +300,14 @@ class Ctx:
         assert not (acc and dact and dact != ACT_RELU)
         if self.L.profiler is not None:
             self.L.profiler.pending_flops = 2.0 * M * N * K
+            self.L.profiler.label = "mode%d M%d N%d K%d" % (mode, M, N, K)
         self.L.tc_gemm(mode, a[0], a[1], w_ptr, ldb, M, N, K, out[0], out[1], bias_ptr, pre[0] if pre else None,
                        pre[1] if pre else 0, aux[0] if aux else None, aux[1] if aux else 0, act, dact, acc, self.stream)
 
     def tc_wgrad(self, dy, x, P, Co, Ci, dw_ptr):
         if self.L.profiler is not None:
             self.L.profiler.pending_flops = 2.0 * P * Co * Ci
+            self.L.profiler.label = "P%d Co%d Ci%d" % (P, Co, Ci)
         self.L.tc_wgrad(dy[0], dy[1], x[0], x[1], P, Co, Ci, dw_ptr, Ci, self.stream)
 
     def colsum(self, x, npix, C, out_ptr):

@@ -24,11 +24,17 @@ class ParamTree(nn.Module):
     def __init__(self, spec):
         super().__init__()
         self._spec = list(spec)
-        self._numel = sum(math.prod(s) for _n, s in self._spec)
+        # every tensor starts on a 64-element boundary of the flat buffers: its bf16 shadow is then 128-byte aligned,
+        # which TMA (16 B) and the vectorised kernels need.  The padding stays zero (zero gradient, zero Adam update).
+        self._offsets, off = {}, 0
+        for name, shape in self._spec:
+            self._offsets[name] = off
+            off += (math.prod(shape) + 63) // 64 * 64
+        self._numel = off
         flat = torch.zeros(self._numel)
-        off = 0
         for name, shape in self._spec:
             n = math.prod(shape)
+            off = self._offsets[name]
             mod = self
             *path, leaf = name.split(".")
             for part in path:
@@ -36,7 +42,6 @@ class ParamTree(nn.Module):
                     mod.add_module(part, nn.Module())
                 mod = getattr(mod, part)
             mod.register_parameter(leaf, nn.Parameter(flat[off:off + n].view(shape)))
-            off += n
         self._flat = flat
         self._flat_grad = None
         self._flat_bf16 = None
@@ -61,22 +66,18 @@ class ParamTree(nn.Module):
         dev = first.device
         ok = self._flat.device == dev and self._flat_grad is not None and self._flat_grad.device == dev
         if ok:
-            off = 0
             for name, shape in self._spec:
-                if params[name].data_ptr() != self._flat.data_ptr() + 4 * off:
+                if params[name].data_ptr() != self._flat.data_ptr() + 4 * self._offsets[name]:
                     ok = False
                     break
-                off += math.prod(shape)
         if not ok:
-            flat = torch.empty(self._numel, dtype=torch.float32, device=dev)
+            flat = torch.zeros(self._numel, dtype=torch.float32, device=dev)
             grad = torch.zeros(self._numel, dtype=torch.float32, device=dev)
-            off = 0
             for name, shape in self._spec:
-                n = math.prod(shape)
+                n, off = math.prod(shape), self._offsets[name]
                 flat[off:off + n].copy_(params[name].data.reshape(-1).float())
                 params[name].data = flat[off:off + n].view(shape)
                 params[name].grad = grad[off:off + n].view(shape)
-                off += n
             self._flat, self._flat_grad, self._plist = flat, grad, None
             self._flat_bf16 = torch.empty(self._numel, dtype=torch.bfloat16, device=dev)
         if self._plist is None:

