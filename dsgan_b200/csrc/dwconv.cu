@@ -88,6 +88,203 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad(const T* __restrict__ x, i
     else if (db) atomicAdd(db + cc, sh[tap][lc]);
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 fast path: each thread owns 8 channels (one 16-byte vector) and a strip of TW output pixels along x, sliding the
+// K-wide window in registers.  Threads of a warp cover consecutive channel groups -> 16 B x 32 = 512 B coalesced rows.
+// Weights of the block's channels are staged in shared memory as [tap][channel] fp32.
+constexpr int TW = 8;
+constexpr int VEC_CB = 128;  // channels per block (16 groups of 8)
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __low2float(h);
+    f[2 * e + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// grid: (strip blocks, channel blocks); block: (groups, strips) with groups*strips = 256
+template <int K>
+__global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, bf16* __restrict__ y, int ldy, int N,
+                                                    int H, int W, int C, int flip, int acc_out) {
+  __shared__ float sw[K * K][VEC_CB];
+  constexpr int P = K / 2;
+  const int c_base = blockIdx.y * VEC_CB;
+  const int cb = min(VEC_CB, C - c_base);
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < K * K * cb; i += 256) {
+    const int tap = i / cb, c = i % cb;
+    sw[tap][c] = __ldg(w + (size_t)(c_base + c) * K * K + (flip ? (K * K - 1 - tap) : tap));
+  }
+  __syncthreads();
+  const int cg = threadIdx.x;  // channel group inside the block
+  if (cg * 8 >= cb) return;
+  const int c0 = c_base + cg * 8;
+  const int strips_x = (W + TW - 1) / TW;
+  const long long strip = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+  if (strip >= (long long)N * H * strips_x) return;
+  const int sx = (int)(strip % strips_x);
+  const int yy = (int)((strip / strips_x) % H);
+  const int n = (int)(strip / ((long long)strips_x * H));
+  const int x0 = sx * TW;
+  float acc[TW][8];
+#pragma unroll
+  for (int i = 0; i < TW; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+  const bf16* xb = x + (size_t)n * H * W * ldx + c0;
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = yy + ky - P;
+    if (iy < 0 || iy >= H) continue;
+    float wr[K][8];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const float4 a = *reinterpret_cast<const float4*>(&sw[ky * K + kx][cg * 8]);
+      const float4 b = *reinterpret_cast<const float4*>(&sw[ky * K + kx][cg * 8 + 4]);
+      wr[kx][0] = a.x; wr[kx][1] = a.y; wr[kx][2] = a.z; wr[kx][3] = a.w;
+      wr[kx][4] = b.x; wr[kx][5] = b.y; wr[kx][6] = b.z; wr[kx][7] = b.w;
+    }
+    const bf16* row = xb + (size_t)iy * W * ldx;
+#pragma unroll
+    for (int xi = 0; xi < TW + K - 1; ++xi) {
+      const int ix = x0 + xi - P;
+      if (ix < 0 || ix >= W) continue;
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)), v);
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ox = xi - kx;
+        if (ox >= 0 && ox < TW) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[ox][e] = fmaf(v[e], wr[kx][e], acc[ox][e]);
+        }
+      }
+    }
+  }
+  float bv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bv[e] = bias ? __ldg(bias + c0 + e) : 0.f;
+  bf16* yb = y + ((size_t)(n * H + yy) * W) * ldy + c0;
+#pragma unroll
+  for (int i = 0; i < TW; ++i) {
+    const int ox = x0 + i;
+    if (ox >= W) break;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = acc[i][e] + bv[e];
+    uint4* dst = reinterpret_cast<uint4*>(yb + (size_t)ox * ldy);
+    if (acc_out) {
+      float old[8];
+      unpack8(*dst, old);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += old[e];
+    }
+    *dst = pack8(o);
+  }
+}
+
+// weight gradient: grid (strip chunks, channel blocks, K) — blockIdx.z = ky; each thread accumulates acc[kx][8]
+template <int K>
+__global__ void __launch_bounds__(256) k_dwconv_wgrad_v8(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
+                                                          int lddy, float* __restrict__ dw, float* __restrict__ db, int N,
+                                                          int H, int W, int C, long long strips_per_block) {
+  __shared__ float sacc[K + 1][VEC_CB];
+  constexpr int P = K / 2;
+  const int ky = blockIdx.z;
+  const int c_base = blockIdx.y * VEC_CB;
+  const int cb = min(VEC_CB, C - c_base);
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K + 1) * VEC_CB; i += 256) (&sacc[0][0])[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x;
+  const bool active = cg * 8 < cb;
+  const int c0 = c_base + cg * 8;
+  const int strips_x = (W + TW - 1) / TW;
+  const long long total = (long long)N * H * strips_x;
+  const long long s_begin = (long long)blockIdx.x * strips_per_block;
+  const long long s_end = min(s_begin + strips_per_block, total);
+  float acc[K][8], accb[8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) accb[e] = 0.f;
+  if (active) {
+    for (long long strip = s_begin + threadIdx.y; strip < s_end; strip += blockDim.y) {
+      const int sx = (int)(strip % strips_x);
+      const int yy = (int)((strip / strips_x) % H);
+      const int n = (int)(strip / ((long long)strips_x * H));
+      const int x0 = sx * TW;
+      const int iy = yy + ky - P;
+      const bool row_ok = iy >= 0 && iy < H;
+      if (!row_ok && ky != 0) continue;
+      float g[TW][8];
+      const bf16* gb = dy + ((size_t)(n * H + yy) * W) * lddy + c0;
+#pragma unroll
+      for (int i = 0; i < TW; ++i) {
+        if (x0 + i < W) unpack8(__ldg(reinterpret_cast<const uint4*>(gb + (size_t)(x0 + i) * lddy)), g[i]);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[i][e] = 0.f;
+        }
+      }
+      if (ky == 0) {
+#pragma unroll
+        for (int i = 0; i < TW; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) accb[e] += g[i][e];
+      }
+      if (!row_ok) continue;
+      const bf16* row = x + ((size_t)(n * H + iy) * W) * ldx + c0;
+#pragma unroll
+      for (int xi = 0; xi < TW + K - 1; ++xi) {
+        const int ix = x0 + xi - P;
+        if (ix < 0 || ix >= W) continue;
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)), v);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int ox = xi - kx;
+          if (ox >= 0 && ox < TW) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[kx][e] = fmaf(v[e], g[ox][e], acc[kx][e]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&sacc[kx][cg * 8 + e], acc[kx][e]);
+    if (ky == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&sacc[K][cg * 8 + e], accb[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K + 1) * cb; i += 256) {
+    const int kx = i / cb, c = i % cb;
+    if (kx < K) atomicAdd(dw + (size_t)(c_base + c) * K * K + ky * K + kx, sacc[kx][c]);
+    else if (db && ky == 0) atomicAdd(db + c_base + c, sacc[K][c]);
+  }
+}
+
+inline bool vec_ok(const void* a, int lda, const void* b, int ldb, int C) {
+  return C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
+}
 }  // namespace
 
 extern "C" {
@@ -95,6 +292,22 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
                      int H, int W, int C, int k, int flip, int accumulate, void* stream) {
   const long long total = (long long)N * H * W * C;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DT_BF16 && vec_ok(x, ld_x, y, ld_y, C)) {
+    const int groups = C >= VEC_CB ? VEC_CB / 8 : C / 8;
+    dim3 block(groups, 256 / groups);
+    const long long strips = (long long)N * H * ((W + TW - 1) / TW);
+    dim3 grid(cdiv(strips, block.y), cdiv(C, VEC_CB));
+#define DWV_CASE(KK)                                                                                             \
+  case KK:                                                                                                       \
+    k_dwconv_v8<KK><<<grid, block, 0, s>>>((const bf16*)x, ld_x, w, bias, (bf16*)y, ld_y, N, H, W, C, flip, accumulate); \
+    break;
+    switch (k) {
+      DWV_CASE(3) DWV_CASE(5) DWV_CASE(7) DWV_CASE(9)
+      default: set_error("dwconv: unsupported k=%d", k); return 1;
+    }
+#undef DWV_CASE
+    return DS_LAUNCHED("dwconv_fwd_v8");
+  }
   const unsigned grid = cdiv(total, 256);
 #define DW_CASE(KK)                                                                                             \
   case KK:                                                                                                      \
@@ -112,6 +325,25 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
 int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float* dw, float* db, int dtype, int N,
                        int H, int W, int C, int k, void* stream) {
   const long long npix = (long long)N * H * W;
+  if (dtype == DT_BF16 && vec_ok(x, ld_x, dy, ld_dy, C)) {
+    const int groups = C >= VEC_CB ? VEC_CB / 8 : C / 8;
+    dim3 block(groups, 256 / groups);
+    const long long strips = (long long)N * H * ((W + TW - 1) / TW);
+    long long per_block = 64 * block.y;  // 64 strips per thread row
+    long long blocks_x = (strips + per_block - 1) / per_block;
+    dim3 grid((unsigned)blocks_x, cdiv(C, VEC_CB), k);
+    cudaStream_t s = (cudaStream_t)stream;
+#define DWGV_CASE(KK)                                                                                            \
+  case KK:                                                                                                       \
+    k_dwconv_wgrad_v8<KK><<<grid, block, 0, s>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, dw, db, N, H, W, C, per_block); \
+    break;
+    switch (k) {
+      DWGV_CASE(3) DWGV_CASE(5) DWGV_CASE(7) DWGV_CASE(9)
+      default: set_error("dwconv_wgrad: unsupported k=%d", k); return 1;
+    }
+#undef DWGV_CASE
+    return DS_LAUNCHED("dwconv_wgrad_v8");
+  }
   const int cl = C < 32 ? C : 32;
   DS_REQUIRE(256 % cl == 0 || cl == 3, "dwconv_wgrad: C=%d unsupported channel tiling", C);
   long long chunk = 2048;

@@ -2,6 +2,7 @@
 // writes; forward and backward.  HBM-bound: warp/thread-private partial sums, one atomic per (block, channel).
 // Reference: networks.py:25 and every nn.InstanceNorm2d in MixConvNeXtML.py (Q1 in SURVEY.md §10).
 #include "common.cuh"
+#include <initializer_list>
 #include "../../include/dsgan_b200.h"
 using namespace dsgan;
 
@@ -134,18 +135,238 @@ __global__ void k_in_bwd_apply(const T* __restrict__ x, int ldx, const float* __
     }
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 fast path: 8 channels (16 bytes) per thread, warp rows of consecutive channel groups (coalesced 512 B), block-level
+// reduction through shared-memory atomics, one global atomic per (block, channel).
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __low2float(h);
+    f[2 * e + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ld8(const bf16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+struct VLanes { int gl, pl, tg, tp; };
+__device__ __forceinline__ VLanes vlanes(int C) {
+  VLanes l;
+  const int groups = C / 8;
+  l.gl = groups < 32 ? groups : 32;
+  l.pl = blockDim.x / l.gl;
+  l.tg = threadIdx.x % l.gl;
+  l.tp = threadIdx.x / l.gl;
+  return l;
+}
+constexpr int VCHUNK = 1024;  // pixels per block
+
+__global__ void __launch_bounds__(256) k_in_stats_v8(const bf16* __restrict__ x, int ldx, long long HW, int C,
+                                                      float* __restrict__ stats) {
+  __shared__ float sacc[2][256];
+  const VLanes l = vlanes(C);
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
+  const bf16* xb = x + (size_t)n * HW * ldx;
+  for (int cb = 0; cb < C; cb += l.gl * 8) {
+    for (int i = threadIdx.x; i < 512; i += 256) (&sacc[0][0])[i] = 0.f;
+    __syncthreads();
+    const int c0 = cb + l.tg * 8;
+    if (l.tp < l.pl && c0 < C) {
+      float k[8], s[8], ss[8];
+      unpack8(ld8(xb + c0), k);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
+      for (long long p = p0 + l.tp; p < p1; p += l.pl) {
+        float v[8];
+        unpack8(ld8(xb + p * ldx + c0), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[e] - k[e]; s[e] += d; ss[e] = fmaf(d, d, ss[e]); }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { atomicAdd(&sacc[0][l.tg * 8 + e], s[e]); atomicAdd(&sacc[1][l.tg * 8 + e], ss[e]); }
+      if (blockIdx.x == 0 && l.tp == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) stats[((size_t)n * C + c0 + e) * 3] = k[e];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < l.gl * 8; i += 256) {
+      if (cb + i < C) {
+        atomicAdd(stats + ((size_t)n * C + cb + i) * 3 + 1, sacc[0][i]);
+        atomicAdd(stats + ((size_t)n * C + cb + i) * 3 + 2, sacc[1][i]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x, int ldx, const float* __restrict__ stats,
+                                                      const bf16* __restrict__ res, int ldr, bf16* __restrict__ y, int ldy,
+                                                      long long HW, int C, int act) {
+  const VLanes l = vlanes(C);
+  if (l.tp >= l.pl) return;
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
+  const size_t base = (size_t)n * HW;
+  const float inv = 1.0f / (float)HW;
+  for (int c0 = l.tg * 8; c0 < C; c0 += l.gl * 8) {
+    float mean[8], rstd[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]);
+    for (long long p = p0 + l.tp; p < p1; p += l.pl) {
+      float v[8], r[8];
+      unpack8(ld8(x + (base + p) * ldx + c0), v);
+      if (res) unpack8(ld8(res + (base + p) * ldr + c0), r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float u = (v[e] - mean[e]) * rstd[e];
+        if (res) u += r[e];
+        v[e] = act_fwd(act, u);
+      }
+      *reinterpret_cast<uint4*>(y + (base + p) * ldy + c0) = pack8(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict__ x, int ldx,
+                                                          const float* __restrict__ stats, const bf16* __restrict__ res,
+                                                          int ldr, const bf16* __restrict__ dy, int lddy, long long HW,
+                                                          int C, int act, float* __restrict__ bst) {
+  __shared__ float sacc[2][256];
+  const VLanes l = vlanes(C);
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
+  const size_t base = (size_t)n * HW;
+  const float inv = 1.0f / (float)HW;
+  for (int cb = 0; cb < C; cb += l.gl * 8) {
+    for (int i = threadIdx.x; i < 512; i += 256) (&sacc[0][0])[i] = 0.f;
+    __syncthreads();
+    const int c0 = cb + l.tg * 8;
+    if (l.tp < l.pl && c0 < C) {
+      float mean[8], rstd[8], sg[8], sgx[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]); sg[e] = sgx[e] = 0.f; }
+      for (long long p = p0 + l.tp; p < p1; p += l.pl) {
+        float v[8], g[8], r[8];
+        unpack8(ld8(x + (base + p) * ldx + c0), v);
+        unpack8(ld8(dy + (base + p) * lddy + c0), g);
+        if (act && res) unpack8(ld8(res + (base + p) * ldr + c0), r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (v[e] - mean[e]) * rstd[e];
+          float gg = g[e];
+          if (act) gg *= act_bwd(act, res ? xh + r[e] : xh);
+          sg[e] += gg;
+          sgx[e] = fmaf(gg, xh, sgx[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { atomicAdd(&sacc[0][l.tg * 8 + e], sg[e]); atomicAdd(&sacc[1][l.tg * 8 + e], sgx[e]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < l.gl * 8; i += 256) {
+      if (cb + i < C) {
+        atomicAdd(bst + ((size_t)n * C + cb + i) * 2, sacc[0][i]);
+        atomicAdd(bst + ((size_t)n * C + cb + i) * 2 + 1, sacc[1][i]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict__ x, int ldx,
+                                                          const float* __restrict__ stats, const bf16* __restrict__ res,
+                                                          int ldr, const bf16* __restrict__ dy, int lddy,
+                                                          const float* __restrict__ bst, bf16* __restrict__ dx, int lddx,
+                                                          int acc_dx, bf16* __restrict__ dres, int lddr, int acc_dres,
+                                                          long long HW, int C, int act) {
+  const VLanes l = vlanes(C);
+  if (l.tp >= l.pl) return;
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
+  const size_t base = (size_t)n * HW;
+  const float inv = 1.0f / (float)HW;
+  for (int c0 = l.tg * 8; c0 < C; c0 += l.gl * 8) {
+    float mean[8], rstd[8], mg[8], mgx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]);
+      mg[e] = bst[((size_t)n * C + c0 + e) * 2] * inv;
+      mgx[e] = bst[((size_t)n * C + c0 + e) * 2 + 1] * inv;
+    }
+    for (long long p = p0 + l.tp; p < p1; p += l.pl) {
+      float v[8], g[8], r[8], o[8];
+      unpack8(ld8(x + (base + p) * ldx + c0), v);
+      unpack8(ld8(dy + (base + p) * lddy + c0), g);
+      if (act && res) unpack8(ld8(res + (base + p) * ldr + c0), r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (v[e] - mean[e]) * rstd[e];
+        if (act) g[e] *= act_bwd(act, res ? xh + r[e] : xh);
+        o[e] = rstd[e] * (g[e] - mg[e] - xh * mgx[e]);
+      }
+      uint4* dp = reinterpret_cast<uint4*>(dx + (base + p) * lddx + c0);
+      if (acc_dx) {
+        float old[8];
+        unpack8(*dp, old);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] += old[e];
+      }
+      *dp = pack8(o);
+      if (dres) {
+        uint4* rp = reinterpret_cast<uint4*>(dres + (base + p) * lddr + c0);
+        if (acc_dres) {
+          float old[8];
+          unpack8(*rp, old);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] += old[e];
+        }
+        *rp = pack8(g);
+      }
+    }
+  }
+}
+
+inline bool v8ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
+  if (C % 8) return false;
+  for (const void* p : ptrs) if (p && ((uintptr_t)p % 16)) return false;
+  for (int l : lds) if (l % 8) return false;
+  return true;
+}
 }  // namespace
 
 extern "C" {
 int dsgan_inorm_stats(const void* x, int ld_x, int dtype, int N, long long HW, int C, float* stats, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(stats, 0, sizeof(float) * 3 * N * C, s);
+  if (dtype == DT_BF16 && v8ok(C, {x}, {ld_x})) {
+    dim3 g8(cdiv(HW, VCHUNK), N);
+    k_in_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, HW, C, stats);
+    return DS_LAUNCHED("inorm_stats_v8");
+  }
   dim3 grid(cdiv(HW, CHUNK), N);
   DS_DISPATCH_DT(dtype, (k_in_stats<T><<<grid, 256, 0, s>>>((const T*)x, ld_x, HW, C, stats)));
   return DS_LAUNCHED("inorm_stats");
 }
 int dsgan_inorm_apply(const void* x, int ld_x, const float* stats, const void* res, int ld_res, void* y, int ld_y,
                       int dtype, int N, long long HW, int C, int act, void* stream) {
+  if (dtype == DT_BF16 && v8ok(C, {x, res, y}, {ld_x, res ? ld_res : 0, ld_y})) {
+    dim3 g8(cdiv(HW, VCHUNK), N);
+    k_in_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (bf16*)y,
+                                                        ld_y, HW, C, act);
+    return DS_LAUNCHED("inorm_apply_v8");
+  }
   dim3 grid(cdiv(HW, CHUNK), N);
   DS_DISPATCH_DT(dtype, (k_in_apply<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld_x, stats, (const T*)res,
                                                                               ld_res, (T*)y, ld_y, HW, C, act)));
@@ -155,6 +376,12 @@ int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const voi
                           int ld_dy, int dtype, int N, long long HW, int C, int act, float* bstats, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * N * C, s);
+  if (dtype == DT_BF16 && v8ok(C, {x, res, dy}, {ld_x, res ? ld_res : 0, ld_dy})) {
+    dim3 g8(cdiv(HW, VCHUNK), N);
+    k_in_bwd_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (const bf16*)dy, ld_dy, HW,
+                                          C, act, bstats);
+    return DS_LAUNCHED("inorm_bwd_stats_v8");
+  }
   dim3 grid(cdiv(HW, CHUNK), N);
   DS_DISPATCH_DT(dtype, (k_in_bwd_stats<T><<<grid, 256, 0, s>>>((const T*)x, ld_x, stats, (const T*)res, ld_res,
                                                                (const T*)dy, ld_dy, HW, C, act, bstats)));
@@ -163,6 +390,13 @@ int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const voi
 int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const void* res, int ld_res, const void* dy,
                           int ld_dy, const float* bstats, void* dx, int ld_dx, int acc_dx, void* dres, int ld_dres,
                           int acc_dres, int dtype, int N, long long HW, int C, int act, void* stream) {
+  if (dtype == DT_BF16 && v8ok(C, {x, res, dy, dx, dres}, {ld_x, res ? ld_res : 0, ld_dy, ld_dx, dres ? ld_dres : 0})) {
+    dim3 g8(cdiv(HW, VCHUNK), N);
+    k_in_bwd_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
+                                                            (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
+                                                            (bf16*)dres, ld_dres, acc_dres, HW, C, act);
+    return DS_LAUNCHED("inorm_bwd_apply_v8");
+  }
   dim3 grid(cdiv(HW, CHUNK), N);
   DS_DISPATCH_DT(dtype, (k_in_bwd_apply<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
                             (const T*)x, ld_x, stats, (const T*)res, ld_res, (const T*)dy, ld_dy, bstats, (T*)dx, ld_dx,

@@ -58,6 +58,95 @@ __global__ void k_maxpool_bwd(const T* __restrict__ x, int ldx, const T* __restr
     }
 }
 
+
+// bf16 fast paths of MaxPool2d: one thread per (output pixel, 8-channel group)
+__device__ __forceinline__ void unpack8p(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+    f[2 * e] = __low2float(h);
+    f[2 * e + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8p(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void k_maxpool_fwd_v8(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int H, int W, int C,
+                                 int k, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int G = C / 8, Ho = H / k, Wo = W / k;
+  const int c0 = (int)(i % G) * 8;
+  const long long op = i / G;
+  const int ox = (int)(op % Wo);
+  const long long r = op / Wo;
+  const int oy = (int)(r % Ho);
+  const long long n = r / Ho;
+  const bf16* xb = x + ((n * H + (long long)oy * k) * W + (long long)ox * k) * ldx + c0;
+  float m[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      float v[8];
+      unpack8p(__ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kx) * ldx)), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+    }
+  *reinterpret_cast<uint4*>(y + op * ldy + c0) = pack8p(m);
+}
+__global__ void k_maxpool_bwd_v8(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
+                                 bf16* __restrict__ dx, int lddx, int H, int W, int C, int k, int acc, int relu_mask,
+                                 long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int G = C / 8, Ho = H / k, Wo = W / k;
+  const int c0 = (int)(i % G) * 8;
+  const long long op = i / G;
+  const int ox = (int)(op % Wo);
+  const long long r = op / Wo;
+  const int oy = (int)(r % Ho);
+  const long long n = r / Ho;
+  const long long win = (n * H + (long long)oy * k) * W + (long long)ox * k;
+  const bf16* xb = x + win * ldx + c0;
+  float m[8];
+  int am[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; am[e] = 0; }
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      float v[8];
+      unpack8p(__ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kx) * ldx)), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (v[e] > m[e]) { m[e] = v[e]; am[e] = ky * k + kx; }
+    }
+  float g[8];
+  unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + op * lddy + c0)), g);
+  bf16* db = dx + win * lddx + c0;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      uint4* o = reinterpret_cast<uint4*>(db + ((long long)ky * W + kx) * lddx);
+      float v[8], old[8], xv[8];
+      if (acc) unpack8p(*o, old);
+      if (relu_mask) unpack8p(__ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kx) * ldx)), xv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] = (am[e] == ky * k + kx) ? g[e] : 0.f;
+        if (acc) v[e] += old[e];
+        if (relu_mask && !(xv[e] > 0.f)) v[e] = 0.f;
+      }
+      *o = pack8p(v);
+    }
+}
+
 __device__ __forceinline__ unsigned long long pack_max(float v, unsigned p) {
   unsigned u = __float_as_uint(v);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -186,6 +275,11 @@ int dsgan_maxpool_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int
                       void* stream) {
   DS_REQUIRE(k >= 1 && H % k == 0 && W % k == 0, "maxpool: H,W (%d,%d) must be multiples of k=%d", H, W, k);
   const long long total = (long long)N * (H / k) * (W / k) * C;
+  if (dtype == DT_BF16 && C % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
+    k_maxpool_fwd_v8<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C,
+                                                                            k, total / 8);
+    return DS_LAUNCHED("maxpool_fwd_v8");
+  }
   DS_DISPATCH_DT(dtype, (k_maxpool_fwd<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld_x, (T*)y,
                                                                                              ld_y, H, W, C, k, total)));
   return DS_LAUNCHED("maxpool_fwd");
@@ -194,6 +288,12 @@ int dsgan_maxpool_bwd(const void* x, int ld_x, const void* dy, int ld_dy, void* 
                       int W, int C, int k, int accumulate, int relu_mask, void* stream) {
   DS_REQUIRE(k >= 1 && H % k == 0 && W % k == 0, "maxpool: H,W (%d,%d) must be multiples of k=%d", H, W, k);
   const long long total = (long long)N * (H / k) * (W / k) * C;
+  if (dtype == DT_BF16 && C % 8 == 0 && ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && (uintptr_t)x % 16 == 0 &&
+      (uintptr_t)dy % 16 == 0 && (uintptr_t)dx % 16 == 0) {
+    k_maxpool_bwd_v8<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (bf16*)dx, ld_dx, H, W, C, k, accumulate, relu_mask, total / 8);
+    return DS_LAUNCHED("maxpool_bwd_v8");
+  }
   DS_DISPATCH_DT(dtype, (k_maxpool_bwd<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)x, ld_x, (const T*)dy, ld_dy, (T*)dx, ld_dx, H, W, C, k, accumulate, relu_mask,
                             total)));
