@@ -30,6 +30,13 @@ class TcConvDesc(ctypes.Structure):
                [(n, ctypes.c_int) for n in ("ld_aux", "ld_pre", "act", "dact", "accumulate")]
 
 
+class TcWgradDesc(ctypes.Structure):
+    """Mirror of dsgan_tc_wgrad_desc."""
+    _fields_ = [(n, ctypes.c_int) for n in ("N", "Hg", "Wg", "Cg", "ld_g", "Hx", "Wx", "Cx", "ld_x", "x_stride", "ntaps")] + \
+               [("dy", ctypes.c_int * 16), ("dx", ctypes.c_int * 16), ("tap_off", ctypes.c_longlong * 16),
+                ("s_g", ctypes.c_longlong), ("s_x", ctypes.c_longlong)]
+
+
 _SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
             "unsigned long long": ctypes.c_ulonglong, "size_t": ctypes.c_size_t, "unsigned": ctypes.c_uint}
 

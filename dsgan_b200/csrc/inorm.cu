@@ -169,16 +169,16 @@ __device__ __forceinline__ VLanes vlanes(int C) {
   l.tp = threadIdx.x / l.gl;
   return l;
 }
-constexpr int VCHUNK = 1024;  // pixels per block
 
 __global__ void __launch_bounds__(256) k_in_stats_v8(const bf16* __restrict__ x, int ldx, long long HW, int C,
-                                                      float* __restrict__ stats) {
+                                                      float* __restrict__ stats, int VCHUNK) {
   __shared__ float sacc[2][256];
   const VLanes l = vlanes(C);
   const int n = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
   const bf16* xb = x + (size_t)n * HW * ldx;
-  for (int cb = 0; cb < C; cb += l.gl * 8) {
+  {
+    const int cb = blockIdx.z * l.gl * 8;
     for (int i = threadIdx.x; i < 512; i += 256) (&sacc[0][0])[i] = 0.f;
     __syncthreads();
     const int c0 = cb + l.tg * 8;
@@ -213,14 +213,14 @@ __global__ void __launch_bounds__(256) k_in_stats_v8(const bf16* __restrict__ x,
 
 __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x, int ldx, const float* __restrict__ stats,
                                                       const bf16* __restrict__ res, int ldr, bf16* __restrict__ y, int ldy,
-                                                      long long HW, int C, int act) {
+                                                      long long HW, int C, int act, int VCHUNK) {
   const VLanes l = vlanes(C);
   if (l.tp >= l.pl) return;
   const int n = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
   const size_t base = (size_t)n * HW;
   const float inv = 1.0f / (float)HW;
-  for (int c0 = l.tg * 8; c0 < C; c0 += l.gl * 8) {
+  for (int c0 = blockIdx.z * l.gl * 8 + l.tg * 8; c0 < min(C, (int)(blockIdx.z + 1) * l.gl * 8); c0 += l.gl * 8) {
     float mean[8], rstd[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]);
@@ -242,14 +242,15 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
 __global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict__ x, int ldx,
                                                           const float* __restrict__ stats, const bf16* __restrict__ res,
                                                           int ldr, const bf16* __restrict__ dy, int lddy, long long HW,
-                                                          int C, int act, float* __restrict__ bst) {
+                                                          int C, int act, float* __restrict__ bst, int VCHUNK) {
   __shared__ float sacc[2][256];
   const VLanes l = vlanes(C);
   const int n = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
   const size_t base = (size_t)n * HW;
   const float inv = 1.0f / (float)HW;
-  for (int cb = 0; cb < C; cb += l.gl * 8) {
+  {
+    const int cb = blockIdx.z * l.gl * 8;
     for (int i = threadIdx.x; i < 512; i += 256) (&sacc[0][0])[i] = 0.f;
     __syncthreads();
     const int c0 = cb + l.tg * 8;
@@ -290,14 +291,14 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
                                                           int ldr, const bf16* __restrict__ dy, int lddy,
                                                           const float* __restrict__ bst, bf16* __restrict__ dx, int lddx,
                                                           int acc_dx, bf16* __restrict__ dres, int lddr, int acc_dres,
-                                                          long long HW, int C, int act) {
+                                                          long long HW, int C, int act, int VCHUNK) {
   const VLanes l = vlanes(C);
   if (l.tp >= l.pl) return;
   const int n = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
   const size_t base = (size_t)n * HW;
   const float inv = 1.0f / (float)HW;
-  for (int c0 = l.tg * 8; c0 < C; c0 += l.gl * 8) {
+  for (int c0 = blockIdx.z * l.gl * 8 + l.tg * 8; c0 < min(C, (int)(blockIdx.z + 1) * l.gl * 8); c0 += l.gl * 8) {
     float mean[8], rstd[8], mg[8], mgx[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -338,6 +339,16 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
   }
 }
 
+// grid for the v8 kernels: (pixel chunks, N, channel blocks of <=256); the chunk shrinks on small planes so that the
+// launch still spreads over the 148 SMs
+inline dim3 v8grid(long long HW, int N, int C, int* chunk) {
+  const int groups = C / 8, gl = groups < 32 ? groups : 32;
+  const int cblocks = (C + gl * 8 - 1) / (gl * 8);
+  int ch = 1024;
+  while (ch > 64 && ((HW + ch - 1) / ch) * N * cblocks < 592) ch >>= 1;
+  *chunk = ch;
+  return dim3((unsigned)((HW + ch - 1) / ch), N, cblocks);
+}
 inline bool v8ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
   if (C % 8) return false;
   for (const void* p : ptrs) if (p && ((uintptr_t)p % 16)) return false;
@@ -351,8 +362,9 @@ int dsgan_inorm_stats(const void* x, int ld_x, int dtype, int N, long long HW, i
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(stats, 0, sizeof(float) * 3 * N * C, s);
   if (dtype == DT_BF16 && v8ok(C, {x}, {ld_x})) {
-    dim3 g8(cdiv(HW, VCHUNK), N);
-    k_in_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, HW, C, stats);
+    int ch;
+    dim3 g8 = v8grid(HW, N, C, &ch);
+    k_in_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, HW, C, stats, ch);
     return DS_LAUNCHED("inorm_stats_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
@@ -362,9 +374,10 @@ int dsgan_inorm_stats(const void* x, int ld_x, int dtype, int N, long long HW, i
 int dsgan_inorm_apply(const void* x, int ld_x, const float* stats, const void* res, int ld_res, void* y, int ld_y,
                       int dtype, int N, long long HW, int C, int act, void* stream) {
   if (dtype == DT_BF16 && v8ok(C, {x, res, y}, {ld_x, res ? ld_res : 0, ld_y})) {
-    dim3 g8(cdiv(HW, VCHUNK), N);
+    int ch;
+    dim3 g8 = v8grid(HW, N, C, &ch);
     k_in_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (bf16*)y,
-                                                        ld_y, HW, C, act);
+                                                        ld_y, HW, C, act, ch);
     return DS_LAUNCHED("inorm_apply_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
@@ -377,9 +390,10 @@ int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const voi
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * N * C, s);
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy}, {ld_x, res ? ld_res : 0, ld_dy})) {
-    dim3 g8(cdiv(HW, VCHUNK), N);
+    int ch;
+    dim3 g8 = v8grid(HW, N, C, &ch);
     k_in_bwd_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (const bf16*)dy, ld_dy, HW,
-                                          C, act, bstats);
+                                          C, act, bstats, ch);
     return DS_LAUNCHED("inorm_bwd_stats_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
@@ -391,10 +405,11 @@ int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const voi
                           int ld_dy, const float* bstats, void* dx, int ld_dx, int acc_dx, void* dres, int ld_dres,
                           int acc_dres, int dtype, int N, long long HW, int C, int act, void* stream) {
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy, dx, dres}, {ld_x, res ? ld_res : 0, ld_dy, ld_dx, dres ? ld_dres : 0})) {
-    dim3 g8(cdiv(HW, VCHUNK), N);
+    int ch;
+    dim3 g8 = v8grid(HW, N, C, &ch);
     k_in_bwd_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
                                                             (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
-                                                            (bf16*)dres, ld_dres, acc_dres, HW, C, act);
+                                                            (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch);
     return DS_LAUNCHED("inorm_bwd_apply_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);

@@ -221,6 +221,161 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of the same convolutions on tensor cores:
+//   dW[slab t][m][n] += sum over grid positions (img, y, x):  G[img, y, x, m] * X[img, y*xs + dy_t, x*xs + dx_t, n]
+// with G the tensor indexed on the (small) grid and X the tensor read at the tap offset (stride xs).  Both operands are
+// pixel-major in memory, i.e. MN-major UMMA operands whose K dimension is the pixel index: one pipeline stage holds an
+// 8x16 pixel patch (K = 128) of G (2 boxes of 64 channels) and of X (BN/64 boxes).  A tile is (tap, m block, n block, split
+// of the patch range); partial sums are reduced with fp32 atomics straight into the parameter-gradient tensor, addressed
+// with the master weight's own strides (OIHW or IOHW).
+constexpr int WG_STAGES = 3, WG_BK = TH * TW;  // 128 pixels per stage
+
+struct WgradParams {
+  int N, Hg, Wg;
+  int M, Nn;               // channels of G (rows of dW) and of X (cols of dW)
+  int xs;                  // stride of X w.r.t. the grid
+  int ntaps;
+  int dy[MAX_TAPS], dx[MAX_TAPS];
+  long long tap_off[MAX_TAPS];   // element offset of tap t inside the master weight gradient
+  long long s_m, s_n;            // element strides of dW for the G-channel and X-channel index
+  int tiles_y, tiles_x, m_tiles, n_tiles, splits, patches_per_split;
+  float* dW;
+};
+
+template <int BN>
+struct WgSmem {
+  static constexpr int A_BYTES = 2 * WG_BK * 128;          // 2 atoms of 64 channels x 128 pixels
+  static constexpr int B_BYTES = (BN / 64) * WG_BK * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = WG_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_tc_conv_wgrad(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  using SL = WgSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
+  uint64_t* empty = full + WG_STAGES;
+  uint64_t* tfull = empty + WG_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int patches_per_img = p.tiles_y * p.tiles_x;
+  const int total_patches = p.N * patches_per_img;
+  const int num_tiles = p.ntaps * p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int n_blk = r % p.n_tiles; r /= p.n_tiles;
+        const int m_blk = r % p.m_tiles; r /= p.m_tiles;
+        const int t = r % p.ntaps;
+        const int split = r / p.ntaps;
+        const int q0 = split * p.patches_per_split, q1 = min(q0 + p.patches_per_split, total_patches);
+        for (int q = q0; q < q1; ++q) {
+          const int img = q / patches_per_img, t2 = q % patches_per_img;
+          const int y0 = (t2 / p.tiles_x) * TH, x0 = (t2 % p.tiles_x) * TW;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * SL::STAGE_BYTES;
+          uint8_t* sb = sa + SL::A_BYTES;
+          mbar_expect_tx(&full[stage], SL::STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_4d(sa + j * (WG_BK * 128), &tmG, &full[stage], m_blk * BM + j * 64, x0, y0, img);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sb + j * (WG_BK * 128), &tmX, &full[stage], n_blk * BN + j * 64, x0 * p.xs + p.dx[t],
+                        y0 * p.xs + p.dy[t], img);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC = idesc_bf16(BM, BN, true, true);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / (p.n_tiles * p.m_tiles * p.ntaps);
+        const int q0 = split * p.patches_per_split, q1 = min(q0 + p.patches_per_split, total_patches);
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int q = q0; q < q1; ++q) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
+          const uint64_t adesc = smem_desc_sw128(sa, WG_BK * 128, 1024);
+          const uint64_t bdesc = smem_desc_sw128(sa + SL::A_BYTES, WG_BK * 128, 1024);
+#pragma unroll
+          for (int k = 0; k < WG_BK / 16; ++k)
+            umma_bf16(d_tmem, adesc + (uint64_t)((k * 2048) >> 4), bdesc + (uint64_t)((k * 2048) >> 4), IDESC,
+                      (q > q0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty[stage]);
+          if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int n_blk = r % p.n_tiles; r /= p.n_tiles;
+      const int m_blk = r % p.m_tiles; r /= p.m_tiles;
+      const int t = r % p.ntaps;
+      const int row = m_blk * BM + quarter * 32 + lane;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row < p.M) {
+          float* o = p.dW + p.tap_off[t] + (long long)row * p.s_m;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.Nn) atomicAdd(o + (long long)(col0 + j) * p.s_n, __uint_as_float(v[j]));
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BN>(tmem_base);
+  }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------
 struct Key4 {
   const void* base; uint64_t c, w, h, n, ld; uint32_t es;
@@ -340,5 +495,47 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
   if (BN == 128) return launch<128>(ta, tb, p, s);
   if (BN == 64) return launch<64>(ta, tb, p, s);
   return launch<32>(ta, tb, p, s);
+}
+int dsgan_tc_conv_wgrad_supported(int Cg, int Cx, int ld_g, int ld_x) {
+  return Cg >= 64 && Cx >= 64 && Cg % 8 == 0 && Cx % 8 == 0 && ld_g % 8 == 0 && ld_x % 8 == 0;
+}
+
+int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void* X, float* dW, void* stream) {
+  DS_REQUIRE(d && G && X && dW, "tc_conv_wgrad: null argument");
+  DS_REQUIRE(dsgan_tc_conv_wgrad_supported(d->Cg, d->Cx, d->ld_g, d->ld_x), "tc_conv_wgrad: unsupported Cg=%d Cx=%d", d->Cg, d->Cx);
+  DS_REQUIRE(d->ntaps >= 1 && d->ntaps <= MAX_TAPS && (d->x_stride == 1 || d->x_stride == 2), "tc_conv_wgrad: bad taps/stride");
+  DS_REQUIRE(((uintptr_t)G % 16 == 0) && ((uintptr_t)X % 16 == 0), "tc_conv_wgrad: unaligned");
+  const int BN = d->Cx >= 128 ? 128 : 64;
+  CUtensorMap tg, tx;
+  if (map_input(&tg, G, d->N, d->Hg, d->Wg, d->Cg, d->ld_g, 1)) return 1;
+  if (map_input(&tx, X, d->N, d->Hx, d->Wx, d->Cx, d->ld_x, d->x_stride)) return 1;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.M = d->Cg; p.Nn = d->Cx; p.xs = d->x_stride; p.ntaps = d->ntaps;
+  for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.tap_off[t] = d->tap_off[t]; }
+  p.s_m = d->s_g; p.s_n = d->s_x;
+  p.tiles_y = (d->Hg + TH - 1) / TH; p.tiles_x = (d->Wg + TW - 1) / TW;
+  p.m_tiles = (d->Cg + BM - 1) / BM; p.n_tiles = (d->Cx + BN - 1) / BN;
+  const int total_patches = d->N * p.tiles_y * p.tiles_x;
+  const int base = d->ntaps * p.m_tiles * p.n_tiles;
+  int splits = (2 * sms() + base - 1) / base;
+  if (splits > total_patches) splits = total_patches;
+  if (splits < 1) splits = 1;
+  p.patches_per_split = (total_patches + splits - 1) / splits;
+  p.splits = (total_patches + p.patches_per_split - 1) / p.patches_per_split;
+  p.dW = dW;
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long tiles = (long long)base * p.splits;
+  const int grid = tiles < sms() ? (int)tiles : sms();
+  if (BN == 128) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_tc_conv_wgrad<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<128>::TOTAL); attr = true; }
+    k_tc_conv_wgrad<128><<<grid, NUM_THREADS, WgSmem<128>::TOTAL, s>>>(tg, tx, p);
+  } else {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_tc_conv_wgrad<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<64>::TOTAL); attr = true; }
+    k_tc_conv_wgrad<64><<<grid, NUM_THREADS, WgSmem<64>::TOTAL, s>>>(tg, tx, p);
+  }
+  return DS_LAUNCHED("tc_conv_wgrad");
 }
 }

@@ -12,7 +12,7 @@ import ctypes
 
 import torch
 
-from ._lib import ConvDesc, TcConvDesc, lib, require_device
+from ._lib import ConvDesc, TcConvDesc, TcWgradDesc, lib, require_device
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -80,6 +80,7 @@ class Param:
 
 
 FAMILY = {"conv_fwd": "dense", "conv_wgrad": "dense", "tc_gemm": "dense", "tc_wgrad": "dense", "tc_conv": "dense",
+          "tc_conv_wgrad": "dense", "pack_conv_weight": "optim",
           "colsum": "reduce", "dwconv_fwd": "dwconv", "dwconv_wgrad": "dwconv",
           "inorm_stats": "norm", "inorm_apply": "norm", "inorm_bwd_stats": "norm", "inorm_bwd_apply": "norm",
           "maxpool_fwd": "pool", "maxpool_bwd": "pool", "ca_fwd": "ca", "ca_bwd": "ca", "scale_nc_fwd": "ca",
@@ -102,7 +103,8 @@ class Profile:
         e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
         fl, self.pending_flops = self.pending_flops, 0.0
-        return (name + (" " + self.label if FAMILY.get(name) == "dense" else ""), fl, e0)
+        lab, self.label = self.label, ""
+        return (name + (" " + lab if lab else ""), fl, e0)
 
     def detail(self, top=25):
         """[(ms, launches, TFLOP/s, 'abi-name label')] sorted by time."""
@@ -284,8 +286,29 @@ class Ctx:
         self.L.conv_fwd(ctypes.byref(d), xin[0], w_ptr, bias_ptr, out[0], pre[0] if pre else None,
                         aux[0] if aux else None, self.stream)
 
+    def _tc_wgrad_conv(self, geom, xin, dout, dw_ptr, wst):
+        N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+        if self.dt != BF16 or not self.use_tc or k * k > 16 or s not in (1, 2) or k == 1:
+            return False
+        if xin[0] % 16 or dout[0] % 16 or not self.L.cdll.dsgan_tc_conv_wgrad_supported(Co, Ci, dout[1], xin[1]):
+            return False
+        d = TcWgradDesc()
+        d.N, d.Hg, d.Wg, d.Cg, d.ld_g = N, Ho, Wo, Co, dout[1]
+        d.Hx, d.Wx, d.Cx, d.ld_x = Hi, Wi, Ci, xin[1]
+        d.x_stride, d.ntaps = s, k * k
+        for ky in range(k):
+            for kx in range(k):
+                t = ky * k + kx
+                d.dy[t], d.dx[t], d.tap_off[t] = ky - p, kx - p, ky * wst[2] + kx * wst[3]
+        d.s_g, d.s_x = wst[0], wst[1]
+        self._flops(geom)
+        self.L.tc_conv_wgrad(ctypes.byref(d), dout[0], xin[0], dw_ptr, self.stream)
+        return True
+
     def wgrad_raw(self, geom, xin, dout, dw_ptr, wst):
         N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
+        if self._tc_wgrad_conv(geom, xin, dout, dw_ptr, wst):
+            return
         d = self._desc(N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p, False, xin[1], dout[1], wst)
         self._flops(geom)
         self.L.conv_wgrad(ctypes.byref(d), xin[0], dout[0], dw_ptr, self.stream)
@@ -426,10 +449,16 @@ def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
     return y
 
 
+def _label(ctx, x, extra=""):
+    if ctx.L.profiler is not None:
+        ctx.L.profiler.label = "C%d @%dx%d %s" % (x.C, x.H, x.W, extra)
+
+
 def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=True):
     """Depthwise k x k, stride 1, pad k//2 (MixConvNeXtML.py:94-97,220)."""
     y = out if out is not None else ctx.new(x.N, x.H, x.W, x.C)
     L, s = ctx.L, ctx.stream
+    _label(ctx, x, "k%d" % k)
     L.dwconv_fwd(x.ptr, x.ld, w.ptr, b.ptr, y.ptr, y.ld, ctx.dt, x.N, x.H, x.W, x.C, k, 0, 0, s)
     train_w = ctx.param_grads
 
@@ -438,11 +467,13 @@ def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=Tru
         if gi is None:
             return
         if train_w:
+            _label(ctx, x, "k%d" % k)
             L.dwconv_wgrad(x.ptr, x.ld, gi[0], gi[1], w.gptr, b.gptr, ctx.dt, x.N, x.H, x.W, x.C, k, ctx.stream)
         if not need_dx:
             return
         gp, gld, gacc = x.grad_out()
         assert x.fused_act is None
+        _label(ctx, x, "k%d dgrad" % k)
         L.dwconv_fwd(gi[0], gi[1], w.ptr, None, gp, gld, ctx.dt, x.N, x.H, x.W, x.C, k, 1, gacc, ctx.stream)
     ctx.record(bwd)
     return y
@@ -454,8 +485,10 @@ def inorm(ctx: Ctx, x: Var, act=ACT_NONE, res: Var = None, out: Var = None):
     L = ctx.L
     HW = x.H * x.W
     stats = ctx.f32(x.N, x.C, 3)
+    _label(ctx, x)
     L.inorm_stats(x.ptr, x.ld, ctx.dt, x.N, HW, x.C, stats.data_ptr(), ctx.stream)
     rp, rld = (res.ptr, res.ld) if res is not None else (None, 0)
+    _label(ctx, x)
     L.inorm_apply(x.ptr, x.ld, stats.data_ptr(), rp, rld, y.ptr, y.ld, ctx.dt, x.N, HW, x.C, act, ctx.stream)
 
     def bwd():

@@ -126,6 +126,20 @@ typedef struct {
 int dsgan_tc_conv_supported(int Ci, int Co, int ld_in, int ld_out);
 int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, const float* bias, void* out,
                   void* pre_out, const void* aux, void* stream);
+/* tensor-core weight gradient of the same convolutions:
+ *   dW[tap_off[t] + m*s_g + n*s_x] += sum_{img,y,x} G[img,y,x,m] * X[img, y*x_stride + dy[t], x*x_stride + dx[t], n]
+ * G: bf16 NHWC on the (Hg,Wg) grid with Cg channels; X: bf16 NHWC (Hx,Wx) with Cx channels; dW: fp32 master-layout
+ * gradient addressed with its own strides (OIHW for nn.Conv2d, IOHW for nn.ConvTranspose2d). */
+typedef struct {
+  int N, Hg, Wg, Cg, ld_g;
+  int Hx, Wx, Cx, ld_x;
+  int x_stride, ntaps;
+  int dy[16], dx[16];
+  long long tap_off[16];
+  long long s_g, s_x;
+} dsgan_tc_wgrad_desc;
+int dsgan_tc_conv_wgrad_supported(int Cg, int Cx, int ld_g, int ld_x);
+int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void* X, float* dW, void* stream);
 /* dst[slab=ky*kw+kx][o][i] (bf16) = src[o*s_o + i*s_i + ky'*s_ky + kx'*s_kx], (ky',kx') = flipped tap if flip. */
 int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int kh, int kw, long long s_o, long long s_i,
                            long long s_ky, long long s_kx, int flip, void* stream);
