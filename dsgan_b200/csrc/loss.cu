@@ -24,13 +24,13 @@ int ensure_window() {
 __device__ __forceinline__ float sgn(float v) { return (v > 0.f) - (v < 0.f); }
 
 template <typename T>
-__global__ void k_gan_loss(const T* __restrict__ pred, long long n, float target, int mode, float loss_scale,
+__global__ void k_gan_loss(const T* __restrict__ pred, long long n, int ld, float target, int mode, float loss_scale,
                            float* __restrict__ loss, float grad_scale, T* __restrict__ dpred) {
   __shared__ float sh[32];
   float acc = 0.f;
   const float invn = 1.0f / (float)n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float x = ldf(pred + i);
+    const float x = ldf(pred + i * ld);
     float l, g;
     if (mode == 0) {  // BCEWithLogits: max(x,0) - x*t + log1p(exp(-|x|))   (Q12)
       l = fmaxf(x, 0.f) - x * target + log1pf(expf(-fabsf(x)));
@@ -45,7 +45,7 @@ __global__ void k_gan_loss(const T* __restrict__ pred, long long n, float target
       g = 2.f * dlt * sg * (1.f - sg);
     }
     acc += l;
-    if (dpred) stf(dpred + i, g * grad_scale * invn);
+    if (dpred) stf(dpred + i * ld, g * grad_scale * invn);
   }
   acc = block_sum(acc, sh);
   if (threadIdx.x == 0) atomicAdd(loss, acc * loss_scale * invn);
@@ -320,10 +320,10 @@ inline int grid_for(long long n, int block, int cap = 148 * 8) {
 }  // namespace
 
 extern "C" {
-int dsgan_gan_loss(const void* pred, int dtype, long long n, float target, int mode, float loss_scale, float* loss,
-                   float grad_scale, void* dpred, void* stream) {
+int dsgan_gan_loss(const void* pred, int dtype, long long n, int ld, float target, int mode, float loss_scale,
+                   float* loss, float grad_scale, void* dpred, void* stream) {
   DS_DISPATCH_DT(dtype, (k_gan_loss<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
-                            (const T*)pred, n, target, mode, loss_scale, loss, grad_scale, (T*)dpred)));
+                            (const T*)pred, n, ld, target, mode, loss_scale, loss, grad_scale, (T*)dpred)));
   return DS_LAUNCHED("gan_loss");
 }
 int dsgan_l1_loss(const void* a, const void* b, int dtype, long long n, float* loss, float grad_scale, void* da,

@@ -27,7 +27,7 @@ constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, STAGES = 4, NUM_THREADS = 
 
 struct ConvParams {
   int N, Hg, Wg;            // images, grid extent (positions per image)
-  int Ci, Co;
+  int Ci, Co, co_pad;
   int is_, os_, oy0, ox0;   // input stride, output stride, output parity offset
   int Ho, Wo;               // output extent (pixels)
   int ntaps;
@@ -69,7 +69,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int num_tiles = p.N * tiles_per_img * p.n_tiles;
-  const int kc = p.Ci / BK;  // channel blocks per tap
+  const int kc = (p.Ci + BK - 1) / BK;  // channel blocks per tap (TMA zero-fills channels >= Ci)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -99,7 +99,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint8_t* sa = smem + stage * SL::STAGE_BYTES;
             mbar_expect_tx(&full[stage], SL::STAGE_BYTES);
             tma_load_4d(sa, &tmA, &full[stage], c * BK, cx, cy, img);
-            tma_load_2d(sa + SL::A_BYTES, &tmB, &full[stage], c * BK, p.slab[t] * p.Co + n_blk * BN);
+            tma_load_2d(sa + SL::A_BYTES, &tmB, &full[stage], c * BK, p.slab[t] * p.co_pad + n_blk * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -143,6 +143,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int oy = gy * p.os_ + p.oy0, ox = gx * p.os_ + p.ox0;
       const bool row_ok = gy < p.Hg && gx < p.Wg && oy < p.Ho && ox < p.Wo;
       const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+      const bool vec_ok = (p.ldc % 8 == 0) && (!p.aux || p.ld_aux % 8 == 0) && (!p.pre || p.ld_pre % 8 == 0) &&
+                          (((uintptr_t)p.C | (uintptr_t)p.aux | (uintptr_t)p.pre) % 16 == 0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -151,7 +153,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.Co) {
+        if (row_ok && col0 + 32 <= p.Co && vec_ok) {
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -204,6 +206,22 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int q = 0; q < 4; ++q)
             op[q] = make_uint4(pack2(f[q * 8], f[q * 8 + 1]), pack2(f[q * 8 + 2], f[q * 8 + 3]),
                                pack2(f[q * 8 + 4], f[q * 8 + 5]), pack2(f[q * 8 + 6], f[q * 8 + 7]));
+        }
+        if (row_ok && col0 < p.Co && !(col0 + 32 <= p.Co && vec_ok)) {
+          // narrow / unaligned output (Co = 1, 3, 6, 12 ...): guarded scalar epilogue
+          const int nv = min(32, p.Co - col0);
+          bf16* o = reinterpret_cast<bf16*>(p.C) + pix * p.ldc + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < nv) {
+              float f = __uint_as_float(v[j]);
+              if (p.bias) f += __ldg(p.bias + col0 + j);
+              if (p.accumulate) f += __bfloat162float(o[j]);
+              if (p.dact) f *= act_bwd(p.dact, __bfloat162float(reinterpret_cast<const bf16*>(p.aux)[pix * p.ld_aux + col0 + j]));
+              if (p.pre) reinterpret_cast<bf16*>(p.pre)[pix * p.ld_pre + col0 + j] = __float2bfloat16_rn(f);
+              o[j] = __float2bfloat16_rn(act_fwd(p.act, f));
+            }
+          }
         }
         __syncwarp();
       }
@@ -440,33 +458,38 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cuda
 }
 
 // dst[slab][o][i] (bf16) = src[o*so + i*si + tap_offset(slab)]  — packs OIHW / IOHW fp32 weights into K-major slabs
-__global__ void k_pack_slabs(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int kh, int kw,
-                             long long so, long long si, long long sky, long long skx, int flip) {
-  const long long total = (long long)kh * kw * O * I;
+__global__ void k_pack_slabs(const float* __restrict__ src, bf16* __restrict__ dst, int O, int I, int Op, int Ip,
+                             int kh, int kw, long long so, long long si, long long sky, long long skx, int flip) {
+  const long long total = (long long)kh * kw * Op * Ip;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx % I);
-    const int o = (int)((idx / I) % O);
-    const int slab = (int)(idx / ((long long)I * O));
+    const int i = (int)(idx % Ip);
+    const int o = (int)((idx / Ip) % Op);
+    const int slab = (int)(idx / ((long long)Ip * Op));
     int ky = slab / kw, kx = slab % kw;
     if (flip) { ky = kh - 1 - ky; kx = kw - 1 - kx; }
-    dst[idx] = __float2bfloat16_rn(src[o * so + i * si + ky * sky + kx * skx]);
+    const float v = (o < O && i < I) ? src[o * so + i * si + ky * sky + kx * skx] : 0.f;  // zero padding rows/cols
+    dst[idx] = __float2bfloat16_rn(v);
   }
 }
 }  // namespace
 
 extern "C" {
-int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int kh, int kw, long long s_o, long long s_i,
-                           long long s_ky, long long s_kx, int flip, void* stream) {
-  const long long total = (long long)kh * kw * O * I;
+int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int O_pad, int I_pad, int kh, int kw,
+                           long long s_o, long long s_i, long long s_ky, long long s_kx, int flip, void* stream) {
+  DS_REQUIRE(O_pad >= O && I_pad >= I && I_pad % 64 == 0, "pack_conv_weight: bad padding %d>=%d %d>=%d", O_pad, O, I_pad, I);
+  const long long total = (long long)kh * kw * O_pad * I_pad;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_pack_slabs<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, O, I, kh, kw, s_o, s_i, s_ky, s_kx, flip);
+  k_pack_slabs<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, O, I, O_pad, I_pad, kh, kw, s_o, s_i, s_ky,
+                                                                 s_kx, flip);
   return DS_LAUNCHED("pack_conv_weight");
 }
 
 int dsgan_tc_conv_supported(int Ci, int Co, int ld_in, int ld_out) {
-  return (Ci % 64 == 0) && (Co % 32 == 0) && Co >= 32 && (ld_in % 8 == 0) && (ld_out % 8 == 0);
+  // any channel counts: TMA zero-fills input channels >= Ci (the pixel pitch must be 16-byte aligned), the packed weight
+  // slabs are zero-padded, and narrow / unaligned outputs take the scalar epilogue
+  return Ci >= 1 && Co >= 1 && (ld_in % 8 == 0) && ld_out >= Co;
 }
 
 int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, const float* bias, void* out,
@@ -475,15 +498,16 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
   DS_REQUIRE(dsgan_tc_conv_supported(d->Ci, d->Co, d->ld_in, d->ld_out), "tc_conv: unsupported Ci=%d Co=%d", d->Ci, d->Co);
   DS_REQUIRE(d->ntaps >= 1 && d->ntaps <= MAX_TAPS, "tc_conv: ntaps=%d", d->ntaps);
   DS_REQUIRE(d->in_stride == 1 || d->in_stride == 2, "tc_conv: in_stride=%d", d->in_stride);
-  DS_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)w_slabs % 16 == 0) && ((uintptr_t)out % 16 == 0), "tc_conv: unaligned");
+  DS_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)w_slabs % 16 == 0), "tc_conv: unaligned");
+  DS_REQUIRE(d->ci_pad % 64 == 0 && d->ci_pad >= d->Ci && d->co_pad >= d->Co, "tc_conv: bad slab padding");
   DS_REQUIRE(!d->dact || aux, "tc_conv: dact needs aux");
   const int BN = d->Co >= 256 ? 256 : (d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32));
   CUtensorMap ta, tb;
   if (map_input(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in, d->in_stride)) return 1;
-  if (map_weight(&tb, w_slabs, d->Ci, d->nslabs * d->Co, BN)) return 1;
+  if (map_weight(&tb, w_slabs, d->ci_pad, d->nslabs * d->co_pad, BN)) return 1;
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Ci = d->Ci; p.Co = d->Co;
+  p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Ci = d->Ci; p.Co = d->Co; p.co_pad = d->co_pad;
   p.is_ = d->in_stride; p.os_ = d->out_stride; p.oy0 = d->oy0; p.ox0 = d->ox0; p.Ho = d->Ho; p.Wo = d->Wo;
   p.ntaps = d->ntaps;
   for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.slab[t] = d->slab[t]; }
@@ -497,7 +521,7 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
   return launch<32>(ta, tb, p, s);
 }
 int dsgan_tc_conv_wgrad_supported(int Cg, int Cx, int ld_g, int ld_x) {
-  return Cg >= 64 && Cx >= 64 && Cg % 8 == 0 && Cx % 8 == 0 && ld_g % 8 == 0 && ld_x % 8 == 0;
+  return Cg >= 1 && Cx >= 1 && ld_g % 8 == 0 && ld_x % 8 == 0;  // TMA zero-fills channels beyond Cg / Cx
 }
 
 int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void* X, float* dW, void* stream) {

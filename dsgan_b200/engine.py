@@ -46,20 +46,20 @@ class Var:
             if par.parent is None and par.g is None:
                 # a slice is written before its whole parent: start the parent's gradient at zero so that
                 # sibling slices (and later whole-tensor writers) can all accumulate
-                par.g = torch.zeros((par.N, par.H, par.W, par.C), dtype=par.t.dtype, device=par.t.device)
+                par.g = torch.zeros((par.N, par.H, par.W, par.ld), dtype=par.t.dtype, device=par.t.device)
             p, ld, _acc = par.grad_out()
             return p + self.coff * self.es, ld, 1
         if self.g is None:
-            self.g = torch.empty((self.N, self.H, self.W, self.C), dtype=self.t.dtype, device=self.t.device)
-            return self.g.data_ptr(), self.C, 0
-        return self.g.data_ptr(), self.C, 1
+            self.g = torch.empty((self.N, self.H, self.W, self.ld), dtype=self.t.dtype, device=self.t.device)
+            return self.g.data_ptr(), self.ld, 0
+        return self.g.data_ptr(), self.ld, 1
 
     def grad_in(self):
         """-> (ptr, ld) of the accumulated gradient, or None if nothing flowed here."""
         if self.parent is not None:
             r = self.parent.grad_in()
             return None if r is None else (r[0] + self.coff * self.es, r[1])
-        return None if self.g is None else (self.g.data_ptr(), self.C)
+        return None if self.g is None else (self.g.data_ptr(), self.ld)
 
 
 class Param:
@@ -178,7 +178,10 @@ class Ctx:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def new(self, N, H, W, C):
-        return Var(torch.empty((N, H, W, C), dtype=self.tdtype, device=self.device), N, H, W, C)
+        """NHWC activation.  In bf16 mode the pixel pitch of odd channel counts (3, 6, 12, 1) is padded to a multiple
+        of 8 elements (16 bytes) so the tensor can be a TMA source; the pad lanes are never read."""
+        ld = C if (self.dt == F32 or C % 8 == 0) else (C + 7) // 8 * 8
+        return Var(torch.empty((N, H, W, ld), dtype=self.tdtype, device=self.device), N, H, W, C, ld=ld)
 
     def f32(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.device)
@@ -224,14 +227,17 @@ class Ctx:
         return d
 
     def _slabs(self, w, O, I, k, wst):
-        """bf16 [k*k][O][I] K-major slabs of a conv weight for the tcgen05 implicit GEMM, cached per pack epoch."""
+        """bf16 [k*k][O_pad][I_pad] zero-padded K-major slabs of a conv weight for the tcgen05 implicit GEMM, cached per
+        pack epoch.  -> (ptr, O_pad, I_pad)"""
+        Op, Ip = (O + 31) // 32 * 32, (I + 63) // 64 * 64
         key = ("slabs", O, I, wst)
         hit = w.cache.get(key)
         if hit is None or hit[0] != self.pack_epoch:
-            buf = hit[1] if hit is not None else torch.empty(k * k * O * I, dtype=torch.bfloat16, device=self.device)
-            self.L.pack_conv_weight(w.ptr, buf.data_ptr(), O, I, k, k, wst[0], wst[1], wst[2], wst[3], 0, self.stream)
+            buf = hit[1] if hit is not None else torch.empty(k * k * Op * Ip, dtype=torch.bfloat16, device=self.device)
+            self.L.pack_conv_weight(w.ptr, buf.data_ptr(), O, I, Op, Ip, k, k, wst[0], wst[1], wst[2], wst[3], 0,
+                                    self.stream)
             w.cache[key] = hit = (self.pack_epoch, buf)
-        return hit[1].data_ptr()
+        return hit[1].data_ptr(), Op, Ip
 
     def _tc_conv(self, geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):
         """tcgen05 implicit-GEMM path of conv_raw; returns False when the shape is not eligible."""
@@ -240,14 +246,13 @@ class Ctx:
             return False
         if not self.L.cdll.dsgan_tc_conv_supported(Ci, Co, xin[1], out[1]):
             return False
-        ptrs = [xin[0], out[0]] + ([aux[0]] if aux else []) + ([pre[0]] if pre else [])
-        if any(q % 16 for q in ptrs) or (aux and aux[1] % 8) or (pre and pre[1] % 8):
+        if xin[0] % 16:
             return False
-        slabs = self._slabs(w, Co, Ci, k, wst)
+        slabs, co_pad, ci_pad = self._slabs(w, Co, Ci, k, wst)
         d = TcConvDesc()
         d.N, d.Hi, d.Wi, d.Ci, d.ld_in = N, Hi, Wi, Ci, xin[1]
         d.Ho, d.Wo, d.Co, d.ld_out = Ho, Wo, Co, out[1]
-        d.nslabs = k * k
+        d.nslabs, d.co_pad, d.ci_pad = k * k, co_pad, ci_pad
         d.ld_aux, d.ld_pre = (aux[1] if aux else 0), (pre[1] if pre else 0)
         d.act, d.dact, d.accumulate = act, dact, acc
         self._flops(geom)
@@ -277,7 +282,7 @@ class Ctx:
         """geom = (N,Hi,Wi,Ci,Ho,Wo,Co,k,stride,pad); xin/out/aux/pre = (ptr, ld); w = Param (or raw fp32 pointer)."""
         assert not (acc and dact and dact != ACT_RELU), "accumulate+dact is only exact for the idempotent ReLU mask"
         N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
-        if k > 1 and self._tc_conv(geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):
+        if self._tc_conv(geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):
             return
         w_ptr = w.ptr if hasattr(w, "ptr") else w
         d = self._desc(N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p, transposed, xin[1], out[1], wst, act, dact, acc,
@@ -288,7 +293,7 @@ class Ctx:
 
     def _tc_wgrad_conv(self, geom, xin, dout, dw_ptr, wst):
         N, Hi, Wi, Ci, Ho, Wo, Co, k, s, p = geom
-        if self.dt != BF16 or not self.use_tc or k * k > 16 or s not in (1, 2) or k == 1:
+        if self.dt != BF16 or not self.use_tc or k * k > 16 or s not in (1, 2):
             return False
         if xin[0] % 16 or dout[0] % 16 or not self.L.cdll.dsgan_tc_conv_wgrad_supported(Co, Ci, dout[1], xin[1]):
             return False

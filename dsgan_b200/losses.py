@@ -16,15 +16,15 @@ MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)  # MS_SSIM.py:200
 def gan_loss(ctx: Ctx, pred: Var, target_is_real: bool, slot: int, loss_scale=1.0, grad_scale=1.0, use_lsgan=False,
              sigmoid_d=False, want_grad=True):
     """GANLoss.__call__ (networks.py:154-163).  Writes d(loss*grad_scale)/d pred into pred's gradient."""
-    assert pred.ld == pred.C
-    n = pred.npix * pred.C
+    assert pred.C == 1, "PatchGAN logits have one channel"
+    n = pred.npix
     mode = 0 if not use_lsgan else (2 if sigmoid_d else 1)
     gp = None
     if want_grad and not ctx.no_grad:
         gp, gld, gacc = pred.grad_out()
-        assert gacc == 0 and gld == pred.C and pred.fused_act is None
-    ctx.L.gan_loss(pred.ptr, ctx.dt, n, 1.0 if target_is_real else 0.0, mode, loss_scale, slot, grad_scale, gp,
-                   ctx.stream)
+        assert gacc == 0 and gld == pred.ld and pred.fused_act is None
+    ctx.L.gan_loss(pred.ptr, ctx.dt, n, pred.ld, 1.0 if target_is_real else 0.0, mode, loss_scale, slot, grad_scale,
+                   gp, ctx.stream)
 
 
 def l1_images(ctx: Ctx, fake: torch.Tensor, real: torch.Tensor, slot: int, grad_scale, dfake: torch.Tensor):

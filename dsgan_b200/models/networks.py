@@ -160,6 +160,6 @@ class GANLoss(nn.Module):
         x = input.contiguous().float()
         val = torch.zeros(1, dtype=torch.float32, device=input.device)
         t = float(self.real_label if target_is_real else self.fake_label)
-        ctx.L.gan_loss(x.data_ptr(), 0, x.numel(), t, 1 if self.use_lsgan else 0, 1.0, val.data_ptr(), 0.0, None,
+        ctx.L.gan_loss(x.data_ptr(), 0, x.numel(), 1, t, 1 if self.use_lsgan else 0, 1.0, val.data_ptr(), 0.0, None,
                        ctx.stream)
         return val[0]

@@ -134,9 +134,9 @@ class Pix2PixModel(BaseModel):
         losses.ssim_training_loss(ctx, real, fake, self._slot("ssim"), float(self.w_ss), dfake)
         # dL/dfake_B -> generator backward
         ctx.param_grads = True
-        gp, _ld, _acc = self._g_out.grad_out()
+        gp, gld, _acc = self._g_out.grad_out()
         ctx.L.nchw_to_nhwc(dfake.data_ptr(), gp, ctx.dt, fake.shape[0], fake.shape[1], fake.shape[2], fake.shape[3],
-                           self._g_out.C, 1.0, 0.0, ctx.stream)
+                           gld, 1.0, 0.0, ctx.stream)
         ctx.backward(self._g_tape)
         self._g_tape = self._g_out = None
 

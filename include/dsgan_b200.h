@@ -111,7 +111,9 @@ int dsgan_pack_bf16(const float* src, void* dst, long long n, void* stream);
 
 /* tensor-core implicit-GEMM convolution (csrc/tc_conv.cu).  Grid position (y,x) of image n reads input pixel
  * (y*in_stride + dy[t], x*in_stride + dx[t]) for tap t (zero outside the image) against weight slab slab[t], and writes
- * output pixel (y*out_stride + oy0, x*out_stride + ox0).  w_slabs: bf16 [nslabs][Co][Ci] (dsgan_pack_conv_weight).
+ * output pixel (y*out_stride + oy0, x*out_stride + ox0).  w_slabs: bf16 [nslabs][co_pad][ci_pad], zero padded
+ * (dsgan_pack_conv_weight).  Any Ci/Co: the input pixel pitch must be a multiple of 8 elements (TMA zero-fills the
+ * channels >= Ci), narrow outputs (Co = 1, 3, 6 ...) take a scalar epilogue.
  * Covers nn.Conv2d s1/s2 and nn.ConvTranspose2d(s2) forward and input-gradients: models/vgg.py:16-25,
  * networks.py:544-569, MixConvNeXtML.py:53,150.  Epilogue as dsgan_conv_fwd. */
 typedef struct {
@@ -120,6 +122,7 @@ typedef struct {
   int Hg, Wg;
   int in_stride, out_stride, oy0, ox0;
   int ntaps, nslabs;
+  int co_pad, ci_pad; /* row / column padding of the packed slabs (>= Co, >= Ci and a multiple of 64) */
   int dy[16], dx[16], slab[16];
   int ld_aux, ld_pre, act, dact, accumulate;
 } dsgan_tc_conv_desc;
@@ -140,9 +143,10 @@ typedef struct {
 } dsgan_tc_wgrad_desc;
 int dsgan_tc_conv_wgrad_supported(int Cg, int Cx, int ld_g, int ld_x);
 int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void* X, float* dW, void* stream);
-/* dst[slab=ky*kw+kx][o][i] (bf16) = src[o*s_o + i*s_i + ky'*s_ky + kx'*s_kx], (ky',kx') = flipped tap if flip. */
-int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int kh, int kw, long long s_o, long long s_i,
-                           long long s_ky, long long s_kx, int flip, void* stream);
+/* dst[slab=ky*kw+kx][o < O_pad][i < I_pad] (bf16) = src[o*s_o + i*s_i + ky'*s_ky + kx'*s_kx] (0 in the padding),
+ * (ky',kx') = flipped tap if flip. */
+int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int O_pad, int I_pad, int kh, int kw,
+                           long long s_o, long long s_i, long long s_ky, long long s_kx, int flip, void* stream);
 
 /* ---- depthwise convolution (MixConvNeXtML.py:94-97,220: k = 3,5,7,9, stride 1, pad k/2) ---- */
 /* flip=0: forward (w is [C,1,k,k] fp32, bias may be NULL); flip=1: input-gradient (correlate with the
@@ -190,8 +194,8 @@ int dsgan_ca_bwd(const float* ds, const float* s, const float* avg, const float*
 /* GANLoss (networks.py:143-163): mode 0 = BCEWithLogits, 1 = MSE, 2 = MSE on sigmoid(pred) (the `--no_lsgan`
  * pairing of Sigmoid-D + MSELoss, pix2pix_model.py:98,112-114); target is the constant 1.0/0.0.
  * loss[0] += loss_scale*mean(...);  dpred (=) grad_scale * d mean/d pred  (dpred may be NULL). */
-int dsgan_gan_loss(const void* pred, int dtype, long long n, float target, int mode, float loss_scale, float* loss,
-                   float grad_scale, void* dpred, void* stream);
+int dsgan_gan_loss(const void* pred, int dtype, long long n, int ld, float target, int mode, float loss_scale,
+                   float* loss, float grad_scale, void* dpred, void* stream); /* element i lives at pred[i*ld] */
 /* nn.L1Loss (pix2pix_model.py:115,177,182-186): loss[0] += mean|a-b|; da (=|+=) grad_scale*sign(a-b)/n,
  * multiplied by (a>0) when relu_mask (a is a ReLU output whose gradient is kept w.r.t. its pre-activation). */
 int dsgan_l1_loss(const void* a, const void* b, int dtype, long long n, float* loss, float grad_scale, void* da,

@@ -13,9 +13,10 @@ def ctx_for(precision):
 
 
 def to_var(ctx, x_nchw):
-    t = x_nchw.permute(0, 2, 3, 1).contiguous().to("cuda:0", ctx.tdtype)
-    N, H, W, C = t.shape
-    return Var(t, N, H, W, C)
+    N, C, H, W = x_nchw.shape
+    v = ctx.new(N, H, W, C)  # padded pixel pitch for odd channel counts in bf16 mode
+    v.t[..., :C] = x_nchw.permute(0, 2, 3, 1).to("cuda:0", ctx.tdtype)
+    return v
 
 
 def from_nhwc(t):
@@ -23,18 +24,18 @@ def from_nhwc(t):
 
 
 def var_data(v):
-    assert v.ld == v.C
-    return from_nhwc(v.t)
+    assert v.parent is None
+    return from_nhwc(v.t[..., :v.C])
 
 
 def var_grad(v):
-    return from_nhwc(v.g)
+    return from_nhwc(v.g[..., :v.C])
 
 
 def set_grad(ctx, v, dy_nchw):
     gp, ld, acc = v.grad_out()
-    assert acc == 0 and ld == v.C
-    v.g.copy_(dy_nchw.permute(0, 2, 3, 1).contiguous().to("cuda:0", ctx.tdtype))
+    assert acc == 0 and ld == v.ld
+    v.g[..., :v.C] = dy_nchw.permute(0, 2, 3, 1).to("cuda:0", ctx.tdtype)
 
 
 def make_params(tensors):
