@@ -158,12 +158,16 @@ __global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, i
       wr[kx][4] = b.x; wr[kx][5] = b.y; wr[kx][6] = b.z; wr[kx][7] = b.w;
     }
     const bf16* row = xb + (size_t)iy * W * ldx;
+    uint4 rv[TW + K - 1];  // all loads of the row are issued before any is consumed (memory-level parallelism)
 #pragma unroll
     for (int xi = 0; xi < TW + K - 1; ++xi) {
       const int ix = x0 + xi - P;
-      if (ix < 0 || ix >= W) continue;
+      rv[xi] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int xi = 0; xi < TW + K - 1; ++xi) {
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)), v);
+      unpack8(rv[xi], v);
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         const int ox = xi - kx;
@@ -249,12 +253,16 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v8(const bf16* __restrict_
       }
       if (!row_ok) continue;
       const bf16* row = x + ((size_t)(n * H + iy) * W) * ldx + c0;
+      uint4 rv[TW + K - 1];
 #pragma unroll
       for (int xi = 0; xi < TW + K - 1; ++xi) {
         const int ix = x0 + xi - P;
-        if (ix < 0 || ix >= W) continue;
+        rv[xi] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int xi = 0; xi < TW + K - 1; ++xi) {
         float v[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)), v);
+        unpack8(rv[xi], v);
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
           const int ox = xi - kx;
@@ -329,7 +337,10 @@ int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float
     const int groups = C >= VEC_CB ? VEC_CB / 8 : C / 8;
     dim3 block(groups, 256 / groups);
     const long long strips = (long long)N * H * ((W + TW - 1) / TW);
-    long long per_block = 64 * block.y;  // 64 strips per thread row
+    // ~4 waves of blocks over (strip chunks x channel blocks x k), at least one strip per thread row
+    long long want = (4LL * 148 + (long long)cdiv(C, VEC_CB) * k - 1) / ((long long)cdiv(C, VEC_CB) * k);
+    long long per_block = (strips + want - 1) / want;
+    if (per_block < (long long)block.y) per_block = block.y;
     long long blocks_x = (strips + per_block - 1) / per_block;
     dim3 grid((unsigned)blocks_x, cdiv(C, VEC_CB), k);
     cudaStream_t s = (cudaStream_t)stream;

@@ -23,7 +23,7 @@ using namespace dsgan;
 using namespace dsgan::tc;
 
 namespace {
-constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, STAGES = 4, NUM_THREADS = 192, MAX_TAPS = 16;
+constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, STAGES = 4, EPI_WARPS = 8, NUM_THREADS = 64 + 32 * EPI_WARPS, MAX_TAPS = 16;
 
 struct ConvParams {
   int N, Hg, Wg;            // images, grid extent (positions per image)
@@ -75,7 +75,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -133,6 +133,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else {
     const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2, nparts = EPI_WARPS / 4;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
@@ -148,7 +149,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = part; c < BN / 32; c += nparts) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
@@ -291,7 +292,7 @@ k_tc_conv_wgrad(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     tma_prefetch_desc(&tmG);
     tma_prefetch_desc(&tmX);
     for (int i = 0; i < WG_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -357,6 +358,7 @@ k_tc_conv_wgrad(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
     }
   } else {
     const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2, nparts = EPI_WARPS / 4;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int r = tile;
@@ -367,7 +369,7 @@ k_tc_conv_wgrad(const __grid_constant__ CUtensorMap tmG, const __grid_constant__
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = part; c < BN / 32; c += nparts) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();

@@ -64,7 +64,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 namespace {
 
 constexpr int BM = 128, BK = 64, STAGES = 4;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;               // two per TMEM lane quarter, each takes half of the columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct GemmParams {
   int M, N, K;            // problem (K = contraction length)
@@ -112,7 +113,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -187,6 +188,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   } else {
     // ================= epilogue warps (2..5): TMEM -> registers -> global =================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int part = (warp - 2) >> 2, nparts = EPI_WARPS / 4;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
@@ -195,7 +197,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = part; c < BN / 32; c += nparts) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
