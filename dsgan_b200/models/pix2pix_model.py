@@ -8,9 +8,8 @@ the fused Adam (grad_scale = 1/world).  The TV term is a batch SUM in the refere
 so its gradient is pre-scaled by `world` to keep R-rank training equal to single-GPU big-batch math.
 """
 import torch
-import torch.distributed as dist
 
-from .. import losses
+from .. import losses, parallel
 from ..engine import image_to_nhwc, nhwc_grad_to_image
 from ..optim import FlatAdam
 from ..util.image_pool import ImagePool
@@ -43,7 +42,7 @@ class Pix2PixModel(BaseModel):
         self.netG = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.which_model_netG, opt.norm,
                                       not opt.no_dropout, opt.init_type, self.gpu_ids)
         self.ctx = networks.get_ctx(self.device, self.precision)
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.world = parallel.world_size()
         if self.isTrain:
             use_sigmoid = opt.no_lsgan
             d_in = opt.input_nc + opt.output_nc if self.use_condition == 1 else opt.input_nc
@@ -62,7 +61,7 @@ class Pix2PixModel(BaseModel):
             self._loss_init = init.to(self.device)
             if self.world > 1:  # identical replicas: rank 0's initial weights everywhere
                 for net in (self.netG, self.netD, self.vgg):
-                    dist.broadcast(net.flat_buffers()[0], 0)
+                    parallel.broadcast_params(net.flat_buffers()[0], 0)
 
     # ---- reference API ---------------------------------------------------------------------
     def set_input(self, input):
@@ -130,7 +129,7 @@ class Pix2PixModel(BaseModel):
             losses.l1_features(ctx, f, r, self._slot("vgg"), float(self.w_vgg))
         ctx.backward()
         nhwc_grad_to_image(ctx, xv, dfake)
-        losses.tv_loss(ctx, fake, self._slot("tv"), float(self.w_tv) * self.world, dfake)
+        losses.tv_loss(ctx, fake, self._slot("tv"), float(self.w_tv) * parallel.tv_grad_scale(self.world), dfake)
         losses.ssim_training_loss(ctx, real, fake, self._slot("ssim"), float(self.w_ss), dfake)
         # dL/dfake_B -> generator backward
         ctx.param_grads = True
@@ -141,8 +140,7 @@ class Pix2PixModel(BaseModel):
         self._g_tape = self._g_out = None
 
     def _allreduce(self, net):
-        if self.world > 1:
-            dist.all_reduce(net.flat_buffers()[1], op=dist.ReduceOp.SUM)
+        parallel.allreduce_grads(net.flat_buffers()[1])
 
     def optimize_parameters(self):
         self._loss.copy_(self._loss_init)
@@ -152,12 +150,12 @@ class Pix2PixModel(BaseModel):
             self.optimizer_D.zero_grad()
             self.backward_D()
             self._allreduce(self.netD)
-            self.optimizer_D.step(1.0 / self.world)
+            self.optimizer_D.step(parallel.adam_grad_scale(self.world))
         self.set_requires_grad(self.netD, False)
         self.optimizer_G.zero_grad()
         self.backward_G()
         self._allreduce(self.netG)
-        self.optimizer_G.step(1.0 / self.world)
+        self.optimizer_G.step(parallel.adam_grad_scale(self.world))
 
     # ---- loss attributes (0-d device tensors; float() synchronises, like the reference's) -----
     def __getattr__(self, name):
