@@ -290,6 +290,88 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v8(const bf16* __restrict_
   }
 }
 
+
+// weight gradient, single pass over the data: each thread owns TWO channels (one 32-bit load; a warp still covers
+// 64 contiguous channels = 128 B) and ALL K*K taps (2*K*K fp32 accumulators), so dy and x are read once instead of K times.
+template <int K>
+__global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
+                                                          int lddy, float* __restrict__ dw, float* __restrict__ db, int N,
+                                                          int H, int W, int C, long long strips_per_block) {
+  constexpr int CB = 128;  // channels per block (64 pairs)
+  __shared__ float sacc[K * K + 1][CB];
+  constexpr int P = K / 2;
+  const int c_base = blockIdx.y * CB;
+  const int cb = min(CB, C - c_base);
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K * K + 1) * CB; i += 256) (&sacc[0][0])[i] = 0.f;
+  __syncthreads();
+  const int cp = threadIdx.x;
+  const bool active = cp * 2 < cb;
+  const int c0 = c_base + cp * 2;
+  const int strips_x = (W + TW - 1) / TW;
+  const long long total = (long long)N * H * strips_x;
+  const long long s_begin = (long long)blockIdx.x * strips_per_block;
+  const long long s_end = min(s_begin + strips_per_block, total);
+  float acc[K * K][2], accb[2] = {0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < K * K; ++t) acc[t][0] = acc[t][1] = 0.f;
+  if (active) {
+    for (long long strip = s_begin + threadIdx.y; strip < s_end; strip += blockDim.y) {
+      const int sx = (int)(strip % strips_x);
+      const int yy = (int)((strip / strips_x) % H);
+      const int n = (int)(strip / ((long long)strips_x * H));
+      const int x0 = sx * TW;
+      float g[TW][2];
+      const bf16* gb = dy + ((size_t)(n * H + yy) * W) * lddy + c0;
+#pragma unroll
+      for (int i = 0; i < TW; ++i) {
+        if (x0 + i < W) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(gb + (size_t)(x0 + i) * lddy);
+          g[i][0] = __low2float(h); g[i][1] = __high2float(h);
+        } else { g[i][0] = g[i][1] = 0.f; }
+        accb[0] += g[i][0]; accb[1] += g[i][1];
+      }
+#pragma unroll
+      for (int ky = 0; ky < K; ++ky) {
+        const int iy = yy + ky - P;
+        if (iy < 0 || iy >= H) continue;
+        const bf16* row = x + ((size_t)(n * H + iy) * W) * ldx + c0;
+        uint32_t rv[TW + K - 1];
+#pragma unroll
+        for (int xi = 0; xi < TW + K - 1; ++xi) {
+          const int ix = x0 + xi - P;
+          rv[xi] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint32_t*>(row + (size_t)ix * ldx)) : 0u;
+        }
+#pragma unroll
+        for (int xi = 0; xi < TW + K - 1; ++xi) {
+          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rv[xi]);
+          const float v0 = __low2float(h), v1 = __high2float(h);
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const int ox = xi - kx;
+            if (ox >= 0 && ox < TW) {
+              acc[ky * K + kx][0] = fmaf(v0, g[ox][0], acc[ky * K + kx][0]);
+              acc[ky * K + kx][1] = fmaf(v1, g[ox][1], acc[ky * K + kx][1]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) {
+      atomicAdd(&sacc[t][cp * 2], acc[t][0]);
+      atomicAdd(&sacc[t][cp * 2 + 1], acc[t][1]);
+    }
+    atomicAdd(&sacc[K * K][cp * 2], accb[0]);
+    atomicAdd(&sacc[K * K][cp * 2 + 1], accb[1]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K * K + 1) * cb; i += 256) {
+    const int t = i / cb, c = i % cb;
+    if (t < K * K) atomicAdd(dw + (size_t)(c_base + c) * K * K + t, sacc[t][c]);
+    else if (db) atomicAdd(db + c_base + c, sacc[K * K][c]);
+  }
+}
+
 inline bool vec_ok(const void* a, int lda, const void* b, int ldb, int C) {
   return C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
 }
@@ -333,6 +415,27 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
 int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float* dw, float* db, int dtype, int N,
                        int H, int W, int C, int k, void* stream) {
   const long long npix = (long long)N * H * W;
+  if (dtype == DT_BF16 && C % 2 == 0 && ld_x % 2 == 0 && ld_dy % 2 == 0 && ((uintptr_t)x % 4 == 0) && ((uintptr_t)dy % 4 == 0)) {
+    const int pairs = C >= 128 ? 64 : C / 2;
+    dim3 block(pairs, 256 / pairs);
+    const long long strips = (long long)N * H * ((W + TW - 1) / TW);
+    const long long cblocks = cdiv(C, 128);
+    long long want = (4LL * 148 + cblocks - 1) / cblocks;
+    long long per_block = (strips + want - 1) / want;
+    if (per_block < (long long)block.y) per_block = block.y;
+    dim3 grid((unsigned)((strips + per_block - 1) / per_block), (unsigned)cblocks);
+    cudaStream_t s = (cudaStream_t)stream;
+#define DWG2_CASE(KK)                                                                                            \
+  case KK:                                                                                                       \
+    k_dwconv_wgrad_v2<KK><<<grid, block, 0, s>>>((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, dw, db, N, H, W, C, per_block); \
+    break;
+    switch (k) {
+      DWG2_CASE(3) DWG2_CASE(5) DWG2_CASE(7) DWG2_CASE(9)
+      default: set_error("dwconv_wgrad: unsupported k=%d", k); return 1;
+    }
+#undef DWG2_CASE
+    return DS_LAUNCHED("dwconv_wgrad_v2");
+  }
   if (dtype == DT_BF16 && vec_ok(x, ld_x, dy, ld_dy, C)) {
     const int groups = C >= VEC_CB ? VEC_CB / 8 : C / 8;
     dim3 block(groups, 256 / groups);
