@@ -55,6 +55,31 @@ __device__ __forceinline__ float act_bwd(int act, float a) {
   }
 }
 
+// ---- fast GELU for bf16 epilogues ------------------------------------------------------------------------------
+// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): 1 rcp + 1 ex2 + ~8 FMA instead of
+// the ~30-instruction erff.  Used only where the result is rounded to bf16 (tcgen05 epilogues); the fp32 validation
+// mode keeps erff.  gelu'(x) shares the exponential: phi(x) = exp(-x^2/2)/sqrt(2 pi).
+__device__ __forceinline__ void gelu_parts_fast(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);  // = exp(-x^2/2)
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erfz = 1.0f - p * t * e;  // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erfz, x));
+  pdf = 0.39894228040143268f * e;
+}
+__device__ __forceinline__ float act_fwd_fast(int act, float v) {
+  if (act == ACT_GELU) { float c, p; gelu_parts_fast(v, c, p); return v * c; }
+  return act_fwd(act, v);
+}
+__device__ __forceinline__ float act_bwd_fast(int act, float a) {
+  if (act == ACT_GELU) { float c, p; gelu_parts_fast(a, c, p); return fmaf(a, p, c); }
+  return act_bwd(act, a);
+}
+
 // ---- reductions -----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -139,23 +139,24 @@ __global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, i
   const int yy = (int)((strip / strips_x) % H);
   const int n = (int)(strip / ((long long)strips_x * H));
   const int x0 = sx * TW;
-  float acc[TW][8];
+  // packed fp32x2 FMAs (sm_100 FFMA2): two channels per instruction halve the issue count of this issue-bound kernel
+  float2 acc[TW][4];
 #pragma unroll
   for (int i = 0; i < TW; ++i)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+    for (int e = 0; e < 4; ++e) acc[i][e] = make_float2(0.f, 0.f);
   const bf16* xb = x + (size_t)n * H * W * ldx + c0;
 #pragma unroll 1
   for (int ky = 0; ky < K; ++ky) {
     const int iy = yy + ky - P;
     if (iy < 0 || iy >= H) continue;
-    float wr[K][8];
+    float2 wr[K][4];
 #pragma unroll
     for (int kx = 0; kx < K; ++kx) {
       const float4 a = *reinterpret_cast<const float4*>(&sw[ky * K + kx][cg * 8]);
       const float4 b = *reinterpret_cast<const float4*>(&sw[ky * K + kx][cg * 8 + 4]);
-      wr[kx][0] = a.x; wr[kx][1] = a.y; wr[kx][2] = a.z; wr[kx][3] = a.w;
-      wr[kx][4] = b.x; wr[kx][5] = b.y; wr[kx][6] = b.z; wr[kx][7] = b.w;
+      wr[kx][0] = make_float2(a.x, a.y); wr[kx][1] = make_float2(a.z, a.w);
+      wr[kx][2] = make_float2(b.x, b.y); wr[kx][3] = make_float2(b.z, b.w);
     }
     const bf16* row = xb + (size_t)iy * W * ldx;
     uint4 rv[TW + K - 1];  // all loads of the row are issued before any is consumed (memory-level parallelism)
@@ -166,14 +167,16 @@ __global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, i
     }
 #pragma unroll
     for (int xi = 0; xi < TW + K - 1; ++xi) {
-      float v[8];
-      unpack8(rv[xi], v);
+      const uint32_t w4[4] = {rv[xi].x, rv[xi].y, rv[xi].z, rv[xi].w};
+      float2 v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         const int ox = xi - kx;
         if (ox >= 0 && ox < TW) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[ox][e] = fmaf(v[e], wr[kx][e], acc[ox][e]);
+          for (int e = 0; e < 4; ++e) acc[ox][e] = __ffma2_rn(v[e], wr[kx][e], acc[ox][e]);
         }
       }
     }
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, i
     if (ox >= W) break;
     float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = acc[i][e] + bv[e];
+    for (int e = 0; e < 4; ++e) { o[2 * e] = acc[i][e].x + bv[2 * e]; o[2 * e + 1] = acc[i][e].y + bv[2 * e + 1]; }
     uint4* dst = reinterpret_cast<uint4*>(yb + (size_t)ox * ldy);
     if (acc_out) {
       float old[8];
@@ -311,24 +314,23 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
   const long long total = (long long)N * H * strips_x;
   const long long s_begin = (long long)blockIdx.x * strips_per_block;
   const long long s_end = min(s_begin + strips_per_block, total);
-  float acc[K * K][2], accb[2] = {0.f, 0.f};
+  float2 acc[K * K];
+  float accb[2] = {0.f, 0.f};
 #pragma unroll
-  for (int t = 0; t < K * K; ++t) acc[t][0] = acc[t][1] = 0.f;
+  for (int t = 0; t < K * K; ++t) acc[t] = make_float2(0.f, 0.f);
   if (active) {
     for (long long strip = s_begin + threadIdx.y; strip < s_end; strip += blockDim.y) {
       const int sx = (int)(strip % strips_x);
       const int yy = (int)((strip / strips_x) % H);
       const int n = (int)(strip / ((long long)strips_x * H));
       const int x0 = sx * TW;
-      float g[TW][2];
+      float2 g[TW];
       const bf16* gb = dy + ((size_t)(n * H + yy) * W) * lddy + c0;
 #pragma unroll
       for (int i = 0; i < TW; ++i) {
-        if (x0 + i < W) {
-          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(gb + (size_t)(x0 + i) * lddy);
-          g[i][0] = __low2float(h); g[i][1] = __high2float(h);
-        } else { g[i][0] = g[i][1] = 0.f; }
-        accb[0] += g[i][0]; accb[1] += g[i][1];
+        g[i] = (x0 + i < W) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gb + (size_t)(x0 + i) * lddy))
+                            : make_float2(0.f, 0.f);
+        accb[0] += g[i].x; accb[1] += g[i].y;
       }
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
@@ -343,23 +345,19 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
         }
 #pragma unroll
         for (int xi = 0; xi < TW + K - 1; ++xi) {
-          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rv[xi]);
-          const float v0 = __low2float(h), v1 = __high2float(h);
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rv[xi]));
 #pragma unroll
           for (int kx = 0; kx < K; ++kx) {
             const int ox = xi - kx;
-            if (ox >= 0 && ox < TW) {
-              acc[ky * K + kx][0] = fmaf(v0, g[ox][0], acc[ky * K + kx][0]);
-              acc[ky * K + kx][1] = fmaf(v1, g[ox][1], acc[ky * K + kx][1]);
-            }
+            if (ox >= 0 && ox < TW) acc[ky * K + kx] = __ffma2_rn(v, g[ox], acc[ky * K + kx]);
           }
         }
       }
     }
 #pragma unroll
     for (int t = 0; t < K * K; ++t) {
-      atomicAdd(&sacc[t][cp * 2], acc[t][0]);
-      atomicAdd(&sacc[t][cp * 2 + 1], acc[t][1]);
+      atomicAdd(&sacc[t][cp * 2], acc[t].x);
+      atomicAdd(&sacc[t][cp * 2 + 1], acc[t].y);
     }
     atomicAdd(&sacc[K * K][cp * 2], accb[0]);
     atomicAdd(&sacc[K * K][cp * 2 + 1], accb[1]);

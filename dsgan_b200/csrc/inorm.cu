@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256) k_in_stats_v8(const bf16* __restrict__ x,
       unpack8(ld8(xb + c0), k);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
+#pragma unroll 4
       for (long long p = p0 + l.tp; p < p1; p += l.pl) {
         float v[8];
         unpack8(ld8(xb + p * ldx + c0), v);
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
     float mean[8], rstd[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]);
+#pragma unroll 4
     for (long long p = p0 + l.tp; p < p1; p += l.pl) {
       float v[8], r[8];
       unpack8(ld8(x + (base + p) * ldx + c0), v);
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict_
       float mean[8], rstd[8], sg[8], sgx[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) { mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]); sg[e] = sgx[e] = 0.f; }
+#pragma unroll 4
       for (long long p = p0 + l.tp; p < p1; p += l.pl) {
         float v[8], g[8], r[8];
         unpack8(ld8(x + (base + p) * ldx + c0), v);
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
       mg[e] = bst[((size_t)n * C + c0 + e) * 2] * inv;
       mgx[e] = bst[((size_t)n * C + c0 + e) * 2 + 1] * inv;
     }
+#pragma unroll 2
     for (long long p = p0 + l.tp; p < p1; p += l.pl) {
       float v[8], g[8], r[8], o[8];
       unpack8(ld8(x + (base + p) * ldx + c0), v);

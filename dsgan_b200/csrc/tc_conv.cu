@@ -186,8 +186,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                f[q * 8 + e * 2] *= act_bwd(p.dact, __low2float(h));
-                f[q * 8 + e * 2 + 1] *= act_bwd(p.dact, __high2float(h));
+                f[q * 8 + e * 2] *= act_bwd_fast(p.dact, __low2float(h));
+                f[q * 8 + e * 2 + 1] *= act_bwd_fast(p.dact, __high2float(h));
               }
             }
           }
@@ -200,7 +200,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           if (p.act) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_fwd(p.act, f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = act_fwd_fast(p.act, f[j]);
           }
           uint4* op = reinterpret_cast<uint4*>(o);
 #pragma unroll
@@ -218,9 +218,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               float f = __uint_as_float(v[j]);
               if (p.bias) f += __ldg(p.bias + col0 + j);
               if (p.accumulate) f += __bfloat162float(o[j]);
-              if (p.dact) f *= act_bwd(p.dact, __bfloat162float(reinterpret_cast<const bf16*>(p.aux)[pix * p.ld_aux + col0 + j]));
+              if (p.dact) f *= act_bwd_fast(p.dact, __bfloat162float(reinterpret_cast<const bf16*>(p.aux)[pix * p.ld_aux + col0 + j]));
               if (p.pre) reinterpret_cast<bf16*>(p.pre)[pix * p.ld_pre + col0 + j] = __float2bfloat16_rn(f);
-              o[j] = __float2bfloat16_rn(act_fwd(p.act, f));
+              o[j] = __float2bfloat16_rn(act_fwd_fast(p.act, f));
             }
           }
         }

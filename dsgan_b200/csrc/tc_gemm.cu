@@ -240,8 +240,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                f[q * 8 + e * 2] *= act_bwd(p.dact, __low2float(h));
-                f[q * 8 + e * 2 + 1] *= act_bwd(p.dact, __high2float(h));
+                f[q * 8 + e * 2] *= act_bwd_fast(p.dact, __low2float(h));
+                f[q * 8 + e * 2 + 1] *= act_bwd_fast(p.dact, __high2float(h));
               }
             }
           }
@@ -254,7 +254,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           if (p.act) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_fwd(p.act, f[j]);
+            for (int j = 0; j < 32; ++j) f[j] = act_fwd_fast(p.act, f[j]);
           }
           uint4* op = reinterpret_cast<uint4*>(o);
 #pragma unroll

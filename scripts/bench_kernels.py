@@ -29,7 +29,12 @@ def flush_l2():
     FLUSH.zero_()
 
 
+ITERS, WARM = None, None
+
+
 def timeit(fn, iters=10, warm=3, flush=True):
+    iters = ITERS if ITERS is not None else iters
+    warm = WARM if WARM is not None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -75,7 +80,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernels.jsonl"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--iters", type=int, default=None, help="override timed iterations (1 for ncu captures)")
+    ap.add_argument("--warm", type=int, default=None)
     args = ap.parse_args()
+    global ITERS, WARM
+    ITERS, WARM = args.iters, args.warm
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     out = open(args.out, "w")
     ctx = Ctx("cuda:0", "bf16")
