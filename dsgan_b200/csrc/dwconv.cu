@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, i
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[i][e] = make_float2(0.f, 0.f);
   const bf16* xb = x + (size_t)n * H * W * ldx + c0;
+  const bool x_interior = (x0 - P >= 0) && (x0 + TW + P <= W);
 #pragma unroll 1
   for (int ky = 0; ky < K; ++ky) {
     const int iy = yy + ky - P;
@@ -160,10 +161,16 @@ __global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, i
     }
     const bf16* row = xb + (size_t)iy * W * ldx;
     uint4 rv[TW + K - 1];  // all loads of the row are issued before any is consumed (memory-level parallelism)
+    if (x_interior) {      // no per-load bounds predicates away from the left/right image border
+      const bf16* r0 = row + (size_t)(x0 - P) * ldx;
 #pragma unroll
-    for (int xi = 0; xi < TW + K - 1; ++xi) {
-      const int ix = x0 + xi - P;
-      rv[xi] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)) : make_uint4(0, 0, 0, 0);
+      for (int xi = 0; xi < TW + K - 1; ++xi) rv[xi] = __ldg(reinterpret_cast<const uint4*>(r0 + (size_t)xi * ldx));
+    } else {
+#pragma unroll
+      for (int xi = 0; xi < TW + K - 1; ++xi) {
+        const int ix = x0 + xi - P;
+        rv[xi] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint4*>(row + (size_t)ix * ldx)) : make_uint4(0, 0, 0, 0);
+      }
     }
 #pragma unroll
     for (int xi = 0; xi < TW + K - 1; ++xi) {
@@ -324,6 +331,7 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
       const int yy = (int)((strip / strips_x) % H);
       const int n = (int)(strip / ((long long)strips_x * H));
       const int x0 = sx * TW;
+      const bool x_interior = (x0 - P >= 0) && (x0 + TW + P <= W);
       float2 g[TW];
       const bf16* gb = dy + ((size_t)(n * H + yy) * W) * lddy + c0;
 #pragma unroll
@@ -335,13 +343,19 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
         const int iy = yy + ky - P;
-        if (iy < 0 || iy >= H) continue;
+        if (iy < 0 || iy >= H) continue;   // uniform across the warp's strips only at image borders
         const bf16* row = x + ((size_t)(n * H + iy) * W) * ldx + c0;
         uint32_t rv[TW + K - 1];
+        if (x_interior) {
+          const bf16* r0 = row + (size_t)(x0 - P) * ldx;
 #pragma unroll
-        for (int xi = 0; xi < TW + K - 1; ++xi) {
-          const int ix = x0 + xi - P;
-          rv[xi] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint32_t*>(row + (size_t)ix * ldx)) : 0u;
+          for (int xi = 0; xi < TW + K - 1; ++xi) rv[xi] = __ldg(reinterpret_cast<const uint32_t*>(r0 + (size_t)xi * ldx));
+        } else {
+#pragma unroll
+          for (int xi = 0; xi < TW + K - 1; ++xi) {
+            const int ix = x0 + xi - P;
+            rv[xi] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const uint32_t*>(row + (size_t)ix * ldx)) : 0u;
+          }
         }
 #pragma unroll
         for (int xi = 0; xi < TW + K - 1; ++xi) {

@@ -102,6 +102,63 @@ __global__ void k_scale_nc_bwd_apply(const T* __restrict__ dy, const float* __re
   }
 }
 
+// bf16 fast paths: 8 channels (16 B) per thread
+__device__ __forceinline__ void up8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+    f[2 * q] = t.x; f[2 * q + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pk8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+    w[q] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__global__ void k_copy_channels_v8(const bf16* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd, long long npix,
+                                   int G, int acc) {
+  const long long total = npix * G;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / G;
+    const int c = (int)(i - p * G) * 8;
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(src + p * lds + c));
+    uint4* d = reinterpret_cast<uint4*>(dst + p * ldd + c);
+    if (acc) {
+      float a[8], b[8];
+      up8(v, a); up8(*d, b);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] += b[q];
+      v = pk8(a);
+    }
+    *d = v;
+  }
+}
+__global__ void k_add_n_v8(bf16* __restrict__ out, long long n8, const bf16* a, const bf16* b, const bf16* c, const bf16* d,
+                           const bf16* e) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float s[8], t[8];
+    up8(__ldg(reinterpret_cast<const uint4*>(a) + i), s);
+    up8(__ldg(reinterpret_cast<const uint4*>(b) + i), t);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] += t[q];
+    if (c) { up8(__ldg(reinterpret_cast<const uint4*>(c) + i), t);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] += t[q]; }
+    if (d) { up8(__ldg(reinterpret_cast<const uint4*>(d) + i), t);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] += t[q]; }
+    if (e) { up8(__ldg(reinterpret_cast<const uint4*>(e) + i), t);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s[q] += t[q]; }
+    reinterpret_cast<uint4*>(out)[i] = pk8(s);
+  }
+}
+
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = (n + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -124,6 +181,11 @@ int dsgan_nhwc_to_nchw(const void* src, int dtype, int ld_src, float* dst, int N
 }
 int dsgan_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int dtype, long long npix, int C,
                         int accumulate, void* stream) {
+  if (dtype == DT_BF16 && C % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
+    k_copy_channels_v8<<<grid_for(npix * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, ld_src, (bf16*)dst,
+                                                                                        ld_dst, npix, C / 8, accumulate);
+    return DS_LAUNCHED("copy_channels_v8");
+  }
   DS_DISPATCH_DT(dtype, (k_copy_channels<T><<<grid_for(npix * C, 256), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)src, ld_src, (T*)dst, ld_dst, npix, C, accumulate)));
   return DS_LAUNCHED("copy_channels");
@@ -131,6 +193,12 @@ int dsgan_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int 
 int dsgan_add_n(void* out, int dtype, long long n, const void* a, const void* b, const void* c, const void* d,
                 const void* e, void* stream) {
   DS_REQUIRE(a && b, "add_n needs at least two inputs");
+  if (dtype == DT_BF16 && n % 8 == 0 &&
+      (((uintptr_t)out | (uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d | (uintptr_t)e) % 16 == 0)) {
+    k_add_n_v8<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((bf16*)out, n / 8, (const bf16*)a, (const bf16*)b,
+                                                                      (const bf16*)c, (const bf16*)d, (const bf16*)e);
+    return DS_LAUNCHED("add_n_v8");
+  }
   DS_DISPATCH_DT(dtype, (k_add_n<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
                             (T*)out, n, (const T*)a, (const T*)b, (const T*)c, (const T*)d, (const T*)e)));
   return DS_LAUNCHED("add_n");

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
       for (int e = 0; e < 8; ++e) {
         float u = (v[e] - mean[e]) * rstd[e];
         if (res) u += r[e];
-        v[e] = act_fwd(act, u);
+        v[e] = act_fwd_fast(act, u);
       }
       *reinterpret_cast<uint4*>(y + (base + p) * ldy + c0) = pack8(v);
     }
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict_
         for (int e = 0; e < 8; ++e) {
           const float xh = (v[e] - mean[e]) * rstd[e];
           float gg = g[e];
-          if (act) gg *= act_bwd(act, res ? xh + r[e] : xh);
+          if (act) gg *= act_bwd_fast(act, res ? xh + r[e] : xh);
           sg[e] += gg;
           sgx[e] = fmaf(gg, xh, sgx[e]);
         }
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float xh = (v[e] - mean[e]) * rstd[e];
-        if (act) g[e] *= act_bwd(act, res ? xh + r[e] : xh);
+        if (act) g[e] *= act_bwd_fast(act, res ? xh + r[e] : xh);
         o[e] = rstd[e] * (g[e] - mg[e] - xh * mgx[e]);
       }
       uint4* dp = reinterpret_cast<uint4*>(dx + (base + p) * lddx + c0);
