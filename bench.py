@@ -194,7 +194,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     prof = ctx.profile.summary()
     if rank == 0 and args.detail:
-        for ms_, n_, tf_, name_ in ctx.profile.detail(40):
+        for ms_, n_, tf_, name_ in ctx.profile.detail(400):
             print("%9.3f ms  x%-4d %8.1f TF/s  %s" % (ms_, n_, tf_, name_), file=sys.stderr)
     ctx.profile = None
 

@@ -384,6 +384,203 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shared-memory tiled bf16 kernels (the production path): a block stages an (8+K-1) x (32+K-1) x CB input tile with
+// 16-byte cp.async (zero-filled outside the image), then every thread owns ONE channel pair (bf16x2 -> float2, FFMA2)
+// and slides a K-wide register window along x, so each MAC pair costs ~1.4 instructions instead of ~5.
+constexpr int T_TH = 8, T_TW = 32;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// stage rows [y0, y0+rows) x cols [x0, x0+cols) x channels [c_base, c_base+CB) of image n into smem [rows][cols][CB]
+template <int CB>
+__device__ __forceinline__ void stage_tile(bf16* sm, const bf16* __restrict__ src, int ld, int n, int H, int W, int y0, int x0,
+                                           int rows, int cols, int c_base, int C, int tid, int nthreads) {
+  constexpr int OCT = CB / 8;
+  const int total = rows * cols * OCT;
+  for (int i = tid; i < total; i += nthreads) {
+    const int o = i % OCT, px = (i / OCT) % cols, py = i / (OCT * cols);
+    const int gy = y0 + py, gx = x0 + px, c = c_base + o * 8;
+    const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W && c < C;
+    const bf16* g = ok ? src + (((size_t)n * H + gy) * W + gx) * ld + c : src;
+    cp_async16_zfill(sm + ((size_t)py * cols + px) * CB + o * 8, g, ok);
+  }
+}
+
+// forward / input-gradient.  PB = channel pairs per block (CB = 2*PB channels); each thread: one pair, one tile row,
+// XW = PB consecutive output columns.  grid: (tiles_x * tiles_y * N, channel blocks)
+template <int K, int PB>
+__global__ void __launch_bounds__(256) k_dwconv_t(const bf16* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                   const float* __restrict__ bias, bf16* __restrict__ y, int ldy, int N, int H,
+                                                   int W, int C, int flip, int acc_out) {
+  constexpr int CB = 2 * PB, XW = PB, P = K / 2, IR = T_TH + K - 1, IC = T_TW + K - 1;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  bf16* sx = reinterpret_cast<bf16*>(dsm);                       // [IR][IC][CB]
+  float* sw = reinterpret_cast<float*>(dsm + (size_t)IR * IC * CB * 2);  // [K*K][CB]
+  const int tid = threadIdx.x;
+  const int tiles_x = (W + T_TW - 1) / T_TW, tiles_y = (H + T_TH - 1) / T_TH;
+  const int t = blockIdx.x;
+  const int n = t / (tiles_x * tiles_y), ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+  const int y0 = ty * T_TH, x0 = tx * T_TW, c_base = blockIdx.y * CB;
+  stage_tile<CB>(sx, x, ldx, n, H, W, y0 - P, x0 - P, IR, IC, c_base, C, tid, 256);
+  for (int i = tid; i < K * K * CB; i += 256) {
+    const int tap = i / CB, c = i % CB;
+    sw[i] = (c_base + c < C) ? __ldg(w + (size_t)(c_base + c) * K * K + (flip ? K * K - 1 - tap : tap)) : 0.f;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  const int pair = tid % PB, lane = tid / PB;         // lane in [0, 256/PB)
+  const int row = lane % T_TH, cgp = lane / T_TH;      // output row of the tile, column group
+  const int xs = cgp * XW;                             // first output column of this thread inside the tile
+  if (c_base + pair * 2 >= C) return;
+  float2 acc[XW];
+#pragma unroll
+  for (int i = 0; i < XW; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+    float2 wr[K];
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) wr[kx] = *reinterpret_cast<const float2*>(&sw[(ky * K + kx) * CB + pair * 2]);
+    const bf16* rowp = sx + ((size_t)(row + ky) * IC + xs) * CB + pair * 2;
+#pragma unroll
+    for (int xi = 0; xi < XW + K - 1; ++xi) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(rowp + (size_t)xi * CB));
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ox = xi - kx;
+        if (ox >= 0 && ox < XW) acc[ox] = __ffma2_rn(v, wr[kx], acc[ox]);
+      }
+    }
+  }
+  const int gy = y0 + row;
+  if (gy >= H) return;
+  const int c0 = c_base + pair * 2;
+  const float b0 = bias ? __ldg(bias + c0) : 0.f, b1 = bias ? __ldg(bias + c0 + 1) : 0.f;
+  bf16* yb = y + (((size_t)n * H + gy) * W) * ldy + c0;
+#pragma unroll
+  for (int i = 0; i < XW; ++i) {
+    const int gx = x0 + xs + i;
+    if (gx >= W) break;
+    float2 o = make_float2(acc[i].x + b0, acc[i].y + b1);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(yb + (size_t)gx * ldy);
+    if (acc_out) { const float2 old = __bfloat1622float2(*dst); o.x += old.x; o.y += old.y; }
+    *dst = __floats2bfloat162_rn(o.x, o.y);
+  }
+}
+
+// weight gradient.  Thread = (channel pair, ky, row lane); slides along x with a K-wide window of dy.
+// grid: (tile chunks, channel blocks); each block loops over `tiles_per_block` tiles before one reduction.
+template <int K, int PB>
+__global__ void __launch_bounds__(320) k_dwconv_wgrad_t(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
+                                                         int lddy, float* __restrict__ dw, float* __restrict__ db, int N,
+                                                         int H, int W, int C, int tiles_per_block, int RL) {
+  constexpr int CB = 2 * PB, P = K / 2, IR = T_TH + K - 1, IC = T_TW + K - 1;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  bf16* sx = reinterpret_cast<bf16*>(dsm);                                  // [IR][IC][CB]
+  bf16* sg = sx + (size_t)IR * IC * CB;                                     // [T_TH][T_TW][CB]
+  float* sacc = reinterpret_cast<float*>(sg + (size_t)T_TH * T_TW * CB);    // [K*K+1][CB]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < (K * K + 1) * CB; i += nthr) sacc[i] = 0.f;
+  const int tiles_x = (W + T_TW - 1) / T_TW, tiles_y = (H + T_TH - 1) / T_TH;
+  const int total_tiles = N * tiles_x * tiles_y;
+  const int c_base = blockIdx.y * CB;
+  const int pair = tid % PB, ky = (tid / PB) % K, rl = tid / (PB * K);
+  const bool active = rl < RL && (c_base + pair * 2 < C);
+  float2 acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = make_float2(0.f, 0.f);
+  float2 accb = make_float2(0.f, 0.f);
+  const int t_begin = blockIdx.x * tiles_per_block, t_end = min(t_begin + tiles_per_block, total_tiles);
+  for (int t = t_begin; t < t_end; ++t) {
+    const int n = t / (tiles_x * tiles_y), ty = (t / tiles_x) % tiles_y, tx = t % tiles_x;
+    const int y0 = ty * T_TH, x0 = tx * T_TW;
+    __syncthreads();  // previous tile fully consumed
+    stage_tile<CB>(sx, x, ldx, n, H, W, y0 - P, x0 - P, IR, IC, c_base, C, tid, nthr);
+    stage_tile<CB>(sg, dy, lddy, n, H, W, y0, x0, T_TH, T_TW, c_base, C, tid, nthr);
+    cp_async_wait_all();
+    __syncthreads();
+    if (active) {
+      for (int r = rl; r < T_TH; r += RL) {
+        const bf16* xr = sx + ((size_t)(r + ky) * IC) * CB + pair * 2;
+        const bf16* gr = sg + ((size_t)r * T_TW) * CB + pair * 2;
+        float2 gw[K];  // dy window: gw[j] = dy[xi - j]
+#pragma unroll
+        for (int j = 0; j < K; ++j) gw[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int xi = 0; xi < IC; ++xi) {
+#pragma unroll
+          for (int j = K - 1; j > 0; --j) gw[j] = gw[j - 1];
+          gw[0] = (xi < T_TW) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gr + (size_t)xi * CB))
+                              : make_float2(0.f, 0.f);
+          if (ky == 0 && xi < T_TW) { accb.x += gw[0].x; accb.y += gw[0].y; }
+          const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + (size_t)xi * CB));
+          // input column xi pairs with output column ox = xi - kx  ->  tap kx uses dy[xi - kx] = gw[kx]
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) acc[kx] = __ffma2_rn(v, gw[kx], acc[kx]);
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      atomicAdd(&sacc[(ky * K + kx) * CB + pair * 2], acc[kx].x);
+      atomicAdd(&sacc[(ky * K + kx) * CB + pair * 2 + 1], acc[kx].y);
+    }
+    if (ky == 0) {
+      atomicAdd(&sacc[K * K * CB + pair * 2], accb.x);
+      atomicAdd(&sacc[K * K * CB + pair * 2 + 1], accb.y);
+    }
+  }
+  __syncthreads();
+  const int cb = min(CB, C - c_base);
+  for (int i = tid; i < (K * K + 1) * CB; i += nthr) {
+    const int tap = i / CB, c = i % CB;
+    if (c >= cb) continue;
+    if (tap < K * K) atomicAdd(dw + (size_t)(c_base + c) * K * K + tap, sacc[i]);
+    else if (db) atomicAdd(db + c_base + c, sacc[i]);
+  }
+}
+
+template <int K, int PB>
+int launch_dw_t(const bf16* x, int ldx, const float* w, const float* bias, bf16* y, int ldy, int N, int H, int W, int C,
+                int flip, int acc, cudaStream_t s) {
+  constexpr int CB = 2 * PB;
+  const size_t smem = (size_t)(T_TH + K - 1) * (T_TW + K - 1) * CB * 2 + (size_t)K * K * CB * 4;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_dwconv_t<K, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  dim3 grid((unsigned)(N * cdiv(H, T_TH) * cdiv(W, T_TW)), (unsigned)cdiv(C, CB));
+  k_dwconv_t<K, PB><<<grid, 256, smem, s>>>(x, ldx, w, bias, y, ldy, N, H, W, C, flip, acc);
+  return DS_LAUNCHED("dwconv_t");
+}
+template <int K, int PB>
+int launch_dwg_t(const bf16* x, int ldx, const bf16* dy, int lddy, float* dw, float* db, int N, int H, int W, int C,
+                 cudaStream_t s) {
+  constexpr int CB = 2 * PB;
+  const size_t smem = ((size_t)(T_TH + K - 1) * (T_TW + K - 1) + (size_t)T_TH * T_TW) * CB * 2 + (size_t)(K * K + 1) * CB * 4;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_dwconv_wgrad_t<K, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  int RL = 320 / (PB * K);
+  if (RL < 1) RL = 1;
+  if (RL > T_TH) RL = T_TH;
+  const int threads = (PB * K * RL + 31) / 32 * 32;
+  const int total_tiles = N * cdiv(H, T_TH) * cdiv(W, T_TW), cblocks = cdiv(C, CB);
+  int want = (3 * 148 + cblocks - 1) / cblocks;
+  int tpb = (total_tiles + want - 1) / want;
+  if (tpb < 1) tpb = 1;
+  dim3 grid((unsigned)cdiv(total_tiles, tpb), (unsigned)cblocks);
+  k_dwconv_wgrad_t<K, PB><<<grid, threads, smem, s>>>(x, ldx, dy, lddy, dw, db, N, H, W, C, tpb, RL);
+  return DS_LAUNCHED("dwconv_wgrad_t");
+}
+
 inline bool vec_ok(const void* a, int lda, const void* b, int ldb, int C) {
   return C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
 }
@@ -394,6 +591,16 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
                      int H, int W, int C, int k, int flip, int accumulate, void* stream) {
   const long long total = (long long)N * H * W * C;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DT_BF16 && vec_ok(x, ld_x, y, ld_y, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) {
+    const bf16* xp = (const bf16*)x; bf16* yp = (bf16*)y;
+#define DWT(KK, PB) return launch_dw_t<KK, PB>(xp, ld_x, w, bias, yp, ld_y, N, H, W, C, flip, accumulate, s);
+#define DWT_K(PB) switch (k) { case 3: DWT(3, PB) case 5: DWT(5, PB) case 7: DWT(7, PB) case 9: DWT(9, PB) default: break; }
+    if (C >= 64) { DWT_K(32) } else if (C == 32) { DWT_K(16) } else if (C == 16) { DWT_K(8) } else { DWT_K(4) }
+#undef DWT_K
+#undef DWT
+    set_error("dwconv: unsupported k=%d", k);
+    return 1;
+  }
   if (dtype == DT_BF16 && vec_ok(x, ld_x, y, ld_y, C)) {
     const int groups = C >= VEC_CB ? VEC_CB / 8 : C / 8;
     dim3 block(groups, 256 / groups);
@@ -427,6 +634,17 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
 int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float* dw, float* db, int dtype, int N,
                        int H, int W, int C, int k, void* stream) {
   const long long npix = (long long)N * H * W;
+  if (dtype == DT_BF16 && vec_ok(x, ld_x, dy, ld_dy, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) {
+    const bf16* xp = (const bf16*)x; const bf16* gp = (const bf16*)dy;
+    cudaStream_t s = (cudaStream_t)stream;
+#define DWG(KK, PB) return launch_dwg_t<KK, PB>(xp, ld_x, gp, ld_dy, dw, db, N, H, W, C, s);
+#define DWG_K(PB) switch (k) { case 3: DWG(3, PB) case 5: DWG(5, PB) case 7: DWG(7, PB) case 9: DWG(9, PB) default: break; }
+    if (C >= 64) { DWG_K(32) } else if (C == 32) { DWG_K(16) } else if (C == 16) { DWG_K(8) } else { DWG_K(4) }
+#undef DWG_K
+#undef DWG
+    set_error("dwconv_wgrad: unsupported k=%d", k);
+    return 1;
+  }
   if (dtype == DT_BF16 && C % 2 == 0 && ld_x % 2 == 0 && ld_dy % 2 == 0 && ((uintptr_t)x % 4 == 0) && ((uintptr_t)dy % 4 == 0)) {
     const int pairs = C >= 128 ? 64 : C / 2;
     dim3 block(pairs, 256 / pairs);
