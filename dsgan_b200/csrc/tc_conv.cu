@@ -13,7 +13,6 @@
 // Same warp-specialised persistent pipeline as tc_gemm.cu (TMA warp / single-thread MMA issuer / 4 epilogue warps,
 // 4-stage smem ring, double-buffered TMEM accumulator).
 #include "tc_common.cuh"
-#include "tc_epilogue.cuh"
 #include "../../include/dsgan_b200.h"
 #include <map>
 #include <mutex>
@@ -47,8 +46,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STAGE_OFF = BAR_OFF + 256;
-  static constexpr int TOTAL = STAGE_OFF + EPI_WARPS * 4096 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -150,28 +148,67 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                           (((uintptr_t)p.C | (uintptr_t)p.aux | (uintptr_t)p.pre) % 16 == 0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      if (vec_ok && p.Co % 32 == 0) {
-        EpiArgs ea;
-        ea.C = reinterpret_cast<bf16*>(p.C); ea.ldc = p.ldc; ea.bias = p.bias;
-        ea.pre = reinterpret_cast<bf16*>(p.pre); ea.ld_pre = p.ld_pre;
-        ea.aux = reinterpret_cast<const bf16*>(p.aux); ea.ld_aux = p.ld_aux;
-        ea.act = p.act; ea.dact = p.dact; ea.accumulate = p.accumulate; ea.ncols = p.Co;
-        uint4* stage = reinterpret_cast<uint4*>(smem + SL::STAGE_OFF) + (warp - 2) * 256;
-        constexpr int GROUPS = (BN + 63) / 64;
-#pragma unroll 1
-        for (int g = part; g < GROUPS; g += nparts) {
-          const int ncol = (BN - g * 64) < 64 ? (BN - g * 64) : 64;
-          epi_group(ea, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 64, ncol, n_blk * BN + g * 64, (int)pix,
-                    row_ok, stage, lane);
-        }
-      } else {
 #pragma unroll 1
       for (int c = part; c < BN / 32; c += nparts) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.Co) {
+        if (row_ok && col0 + 32 <= p.Co && vec_ok) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+          }
+          bf16* o = reinterpret_cast<bf16*>(p.C) + pix * p.ldc + col0;
+          if (p.accumulate) {
+            const uint4* op = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = op[q];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                f[q * 8 + e * 2] += __low2float(h);
+                f[q * 8 + e * 2 + 1] += __high2float(h);
+              }
+            }
+          }
+          if (p.dact) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + pix * p.ld_aux + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = __ldg(ap + q);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                f[q * 8 + e * 2] *= act_bwd_fast(p.dact, __low2float(h));
+                f[q * 8 + e * 2 + 1] *= act_bwd_fast(p.dact, __high2float(h));
+              }
+            }
+          }
+          if (p.pre) {
+            uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.pre) + pix * p.ld_pre + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              pp[q] = make_uint4(pack2(f[q * 8], f[q * 8 + 1]), pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                                 pack2(f[q * 8 + 4], f[q * 8 + 5]), pack2(f[q * 8 + 6], f[q * 8 + 7]));
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = act_fwd_fast(p.act, f[j]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            op[q] = make_uint4(pack2(f[q * 8], f[q * 8 + 1]), pack2(f[q * 8 + 2], f[q * 8 + 3]),
+                               pack2(f[q * 8 + 4], f[q * 8 + 5]), pack2(f[q * 8 + 6], f[q * 8 + 7]));
+        }
+        if (row_ok && col0 < p.Co && !(col0 + 32 <= p.Co && vec_ok)) {
           // narrow / unaligned output (Co = 1, 3, 6, 12 ...): guarded scalar epilogue
           const int nv = min(32, p.Co - col0);
           bf16* o = reinterpret_cast<bf16*>(p.C) + pix * p.ldc + col0;
@@ -188,7 +225,6 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
         }
         __syncwarp();
-      }
       }
       tc_fence_before();
       __syncwarp();

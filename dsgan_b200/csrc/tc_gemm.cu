@@ -9,7 +9,6 @@
 // warps 2..5 = epilogue (one TMEM lane quarter each).  4-stage smem ring (full/empty mbarriers) and a double-buffered
 // TMEM accumulator (tmem_full/tmem_empty) so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "tc_common.cuh"
-#include "tc_epilogue.cuh"
 #include "../../include/dsgan_b200.h"
 #include <map>
 #include <mutex>
@@ -85,8 +84,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int STAGE_OFF = BAR_OFF + 256;                  // EPI_WARPS x 4 KB epilogue staging tiles
-  static constexpr int TOTAL = STAGE_OFF + 8 * 4096 + 1024;      // + slack for 1024-B alignment
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for 1024-B alignment
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -198,35 +196,74 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      if (MODE == 2) {
 #pragma unroll 1
-        for (int c = part; c < BN / 32; c += nparts) {
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
-          tmem_ld_wait();
-          const int col0 = n_blk * BN + c * 32;
-          if (row_ok && col0 < p.N) {
-            float* o = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+      for (int c = part; c < BN / 32; c += nparts) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+        if (MODE == 2) {
+          float* o = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+        } else {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
           }
-          __syncwarp();
+          bf16* o = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + col0;
+          if (p.accumulate) {
+            const uint4* op = reinterpret_cast<const uint4*>(o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = op[q];
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                f[q * 8 + e * 2] += __low2float(h);
+                f[q * 8 + e * 2 + 1] += __high2float(h);
+              }
+            }
+          }
+          if (p.dact) {
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + (size_t)row * p.ld_aux + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = __ldg(ap + q);
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
+                f[q * 8 + e * 2] *= act_bwd_fast(p.dact, __low2float(h));
+                f[q * 8 + e * 2 + 1] *= act_bwd_fast(p.dact, __high2float(h));
+              }
+            }
+          }
+          if (p.pre) {
+            uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.pre) + (size_t)row * p.ld_pre + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              pp[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                                 pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = act_fwd_fast(p.act, f[j]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            op[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                               pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
         }
-      } else {
-        EpiArgs ea;
-        ea.C = reinterpret_cast<bf16*>(p.C); ea.ldc = p.ldc; ea.bias = p.bias;
-        ea.pre = reinterpret_cast<bf16*>(p.pre); ea.ld_pre = p.ld_pre;
-        ea.aux = reinterpret_cast<const bf16*>(p.aux); ea.ld_aux = p.ld_aux;
-        ea.act = p.act; ea.dact = p.dact; ea.accumulate = p.accumulate; ea.ncols = p.N;
-        uint4* stage = reinterpret_cast<uint4*>(smem + SL::STAGE_OFF) + (warp - 2) * 256;
-        constexpr int GROUPS = (BN + 63) / 64;
-#pragma unroll 1
-        for (int g = part; g < GROUPS; g += nparts) {
-          const int ncol = (BN - g * 64) < 64 ? (BN - g * 64) : 64;
-          epi_group(ea, tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + g * 64, ncol, n_blk * BN + g * 64, row, row_ok,
-                    stage, lane);
         }
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge before the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -314,8 +351,6 @@ int dsgan_tc_gemm(int mode, const void* A, int lda, const void* Wt, int ldb, lon
   DS_REQUIRE(dsgan_tc_gemm_supported(mode, M, N, K, lda, ldb, ldc), "tc_gemm: unsupported shape M=%lld N=%d K=%d", M, N, K);
   DS_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)C % 16 == 0), "tc_gemm: unaligned pointer");
   DS_REQUIRE(!dact || aux, "tc_gemm: dact needs aux");
-  DS_REQUIRE((!pre || (((uintptr_t)pre % 16 == 0) && ld_pre % 8 == 0)) && (!aux || (((uintptr_t)aux % 16 == 0) && ld_aux % 8 == 0)),
-             "tc_gemm: pre/aux must be 16-byte aligned with pitches that are multiples of 8");
   const int BN = pick_bn(N);
   CUtensorMap ta, tb;
   if (get_map_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM)) return 1;
