@@ -23,7 +23,7 @@ using namespace dsgan;
 using namespace dsgan::tc;
 
 namespace {
-constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, STAGES = 4, EPI_WARPS = 8, NUM_THREADS = 64 + 32 * EPI_WARPS, MAX_TAPS = 16;
+constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, STAGES = 4, EPI_WARPS = 16, NUM_THREADS = 64 + 32 * EPI_WARPS, MAX_TAPS = 16;
 
 struct ConvParams {
   int N, Hg, Wg;            // images, grid extent (positions per image)

@@ -64,7 +64,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 namespace {
 
 constexpr int BM = 128, BK = 64, STAGES = 4;
-constexpr int EPI_WARPS = 8;               // two per TMEM lane quarter, each takes half of the columns
+constexpr int EPI_WARPS = 16;              // four per TMEM lane quarter, each takes a share of the 32-column chunks
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
 struct GemmParams {
@@ -351,6 +351,8 @@ int dsgan_tc_gemm(int mode, const void* A, int lda, const void* Wt, int ldb, lon
   DS_REQUIRE(dsgan_tc_gemm_supported(mode, M, N, K, lda, ldb, ldc), "tc_gemm: unsupported shape M=%lld N=%d K=%d", M, N, K);
   DS_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)C % 16 == 0), "tc_gemm: unaligned pointer");
   DS_REQUIRE(!dact || aux, "tc_gemm: dact needs aux");
+  DS_REQUIRE((!pre || (((uintptr_t)pre % 16 == 0) && ld_pre % 8 == 0)) && (!aux || (((uintptr_t)aux % 16 == 0) && ld_aux % 8 == 0)),
+             "tc_gemm: pre/aux must be 16-byte aligned with pitches that are multiples of 8");
   const int BN = pick_bn(N);
   CUtensorMap ta, tb;
   if (get_map_2d(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BM)) return 1;
