@@ -80,6 +80,56 @@ __device__ __forceinline__ float act_bwd_fast(int act, float a) {
   return act_bwd(act, a);
 }
 
+// packed (two elements per instruction, sm_100 FFMA2/FMUL2/FADD2) version of the fast GELU parts
+__device__ __forceinline__ void gelu_parts_fast2(float2 x, float2& cdf, float2& pdf) {
+  const float2 z = __fmul2_rn(make_float2(fabsf(x.x), fabsf(x.y)), make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 den = __ffma2_rn(make_float2(0.3275911f, 0.3275911f), z, make_float2(1.0f, 1.0f));
+  const float2 t = make_float2(__fdividef(1.0f, den.x), __fdividef(1.0f, den.y));
+  const float2 a = __fmul2_rn(__fmul2_rn(z, z), make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = make_float2(exp2f(a.x), exp2f(a.y));  // exp(-z^2) = exp(-x^2/2)
+  float2 p = __ffma2_rn(make_float2(1.061405429f, 1.061405429f), t, make_float2(-1.453152027f, -1.453152027f));
+  p = __ffma2_rn(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = __ffma2_rn(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = __ffma2_rn(p, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 pte = __fmul2_rn(__fmul2_rn(p, t), e);
+  const float2 erfz = make_float2(copysignf(1.0f - pte.x, x.x), copysignf(1.0f - pte.y, x.y));
+  cdf = __ffma2_rn(make_float2(0.5f, 0.5f), erfz, make_float2(0.5f, 0.5f));
+  pdf = __fmul2_rn(make_float2(0.39894228040143268f, 0.39894228040143268f), e);
+}
+// v[0..n) <- act(v) / v *= act'(a), two at a time for GELU
+template <int N>
+__device__ __forceinline__ void act_fwd_fast_vec(int act, float (&v)[N]) {
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      float2 c, p;
+      const float2 x = make_float2(v[j], v[j + 1]);
+      gelu_parts_fast2(x, c, p);
+      const float2 r = __fmul2_rn(x, c);
+      v[j] = r.x; v[j + 1] = r.y;
+    }
+  } else if (act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = act_fwd(act, v[j]);
+  }
+}
+template <int N>
+__device__ __forceinline__ void act_bwd_fast_mul(int act, float (&v)[N], const float (&a)[N]) {
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      float2 c, p;
+      const float2 x = make_float2(a[j], a[j + 1]);
+      gelu_parts_fast2(x, c, p);
+      const float2 d = __ffma2_rn(x, p, c);
+      v[j] *= d.x; v[j + 1] *= d.y;
+    }
+  } else if (act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] *= act_bwd(act, a[j]);
+  }
+}
+
 // ---- reductions -----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -234,8 +234,9 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
       for (int e = 0; e < 8; ++e) {
         float u = (v[e] - mean[e]) * rstd[e];
         if (res) u += r[e];
-        v[e] = act_fwd_fast(act, u);
+        v[e] = u;
       }
+      act_fwd_fast_vec<8>(act, v);
       *reinterpret_cast<uint4*>(y + (base + p) * ldy + c0) = pack8(v);
     }
   }
@@ -266,14 +267,12 @@ __global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict_
         unpack8(ld8(x + (base + p) * ldx + c0), v);
         unpack8(ld8(dy + (base + p) * lddy + c0), g);
         if (act && res) unpack8(ld8(res + (base + p) * ldr + c0), r);
+        float xh[8], u[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (v[e] - mean[e]) * rstd[e];
-          float gg = g[e];
-          if (act) gg *= act_bwd_fast(act, res ? xh + r[e] : xh);
-          sg[e] += gg;
-          sgx[e] = fmaf(gg, xh, sgx[e]);
-        }
+        for (int e = 0; e < 8; ++e) { xh[e] = (v[e] - mean[e]) * rstd[e]; u[e] = res ? xh[e] + r[e] : xh[e]; }
+        act_bwd_fast_mul<8>(act, g, u);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { sg[e] += g[e]; sgx[e] = fmaf(g[e], xh[e], sgx[e]); }
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) { atomicAdd(&sacc[0][l.tg * 8 + e], sg[e]); atomicAdd(&sacc[1][l.tg * 8 + e], sgx[e]); }
@@ -315,12 +314,12 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
       unpack8(ld8(x + (base + p) * ldx + c0), v);
       unpack8(ld8(dy + (base + p) * lddy + c0), g);
       if (act && res) unpack8(ld8(res + (base + p) * ldr + c0), r);
+      float xh[8], u[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xh = (v[e] - mean[e]) * rstd[e];
-        if (act) g[e] *= act_bwd_fast(act, res ? xh + r[e] : xh);
-        o[e] = rstd[e] * (g[e] - mg[e] - xh * mgx[e]);
-      }
+      for (int e = 0; e < 8; ++e) { xh[e] = (v[e] - mean[e]) * rstd[e]; u[e] = res ? xh[e] + r[e] : xh[e]; }
+      act_bwd_fast_mul<8>(act, g, u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd[e] * (g[e] - mg[e] - xh[e] * mgx[e]);
       uint4* dp = reinterpret_cast<uint4*>(dx + (base + p) * lddx + c0);
       if (acc_dx) {
         float old[8];

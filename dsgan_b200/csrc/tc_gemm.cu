@@ -213,8 +213,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+            for (int q = 0; q < 8; ++q) {
+              const float4 b4 = __ldg(bp + q);
+              f[q * 4] += b4.x; f[q * 4 + 1] += b4.y; f[q * 4 + 2] += b4.z; f[q * 4 + 3] += b4.w;
+            }
           }
           bf16* o = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + col0;
           if (p.accumulate) {
@@ -233,17 +237,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           if (p.dact) {
             const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + (size_t)row * p.ld_aux + col0);
+            float a[32];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint4 u = __ldg(ap + q);
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                f[q * 8 + e * 2] *= act_bwd_fast(p.dact, __low2float(h));
-                f[q * 8 + e * 2 + 1] *= act_bwd_fast(p.dact, __high2float(h));
+                const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+                a[q * 8 + e * 2] = h.x; a[q * 8 + e * 2 + 1] = h.y;
               }
             }
+            act_bwd_fast_mul<32>(p.dact, f, a);
           }
           if (p.pre) {
             uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.pre) + (size_t)row * p.ld_pre + col0);
@@ -252,10 +257,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               pp[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
                                  pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
           }
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_fwd_fast(p.act, f[j]);
-          }
+          act_fwd_fast_vec<32>(p.act, f);
           uint4* op = reinterpret_cast<uint4*>(o);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
