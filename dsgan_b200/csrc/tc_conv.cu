@@ -23,7 +23,7 @@ using namespace dsgan;
 using namespace dsgan::tc;
 
 namespace {
-constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, STAGES = 4, EPI_WARPS = 16, NUM_THREADS = 64 + 32 * EPI_WARPS, MAX_TAPS = 16;
+constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, EPI_WARPS = 16, NUM_THREADS = 64 + 32 * EPI_WARPS, MAX_TAPS = 16;
 
 struct ConvParams {
   int N, Hg, Wg;            // images, grid extent (positions per image)
@@ -45,6 +45,7 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);  // keep ~190 KB in flight
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
@@ -61,8 +62,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + SL::STAGES;
+  uint64_t* tfull = empty + SL::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -74,7 +75,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < SL::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -100,7 +101,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_expect_tx(&full[stage], SL::STAGE_BYTES);
             tma_load_4d(sa, &tmA, &full[stage], c * BK, cx, cy, img);
             tma_load_2d(sa + SL::A_BYTES, &tmB, &full[stage], c * BK, p.slab[t] * p.co_pad + n_blk * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == SL::STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -125,7 +126,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == SL::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -63,7 +63,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64;
 constexpr int EPI_WARPS = 16;              // four per TMEM lane quarter, each takes a share of the 32-column chunks
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 
@@ -83,6 +83,8 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // the ring is latency-bound (TMA round trip ~1-2 us): keep ~190 KB in flight -> 8 / 6 / 4 stages for BN = 64 / 128 / 256
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for 1024-B alignment
 };
@@ -101,8 +103,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + SL::STAGES;
+  uint64_t* tfull = empty + SL::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -112,7 +114,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < SL::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -147,7 +149,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           } else {
             tma_load_2d(sb, &tmB, &full[stage], kb * BK, n_blk * BN);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == SL::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -179,7 +181,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                       (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == SL::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);      // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
