@@ -92,7 +92,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DS-GAN G+D training step, 256x256, CPU oracle (port of the reference path)",
+        "config": {"workload": "DS-GAN training step (MixConvNeXtML G + PatchGAN D + VGG/L1/TV/SSIM losses, 2x Adam), "
+                               "256x256, random-init weights; CPU oracle (port of the reference's torch-CPU path), "
+                               "bounded sample of %d images per step" % b,
                    "images_per_step": b},
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))

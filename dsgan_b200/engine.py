@@ -64,11 +64,16 @@ class Var:
 
 class Param:
     """fp32 master parameter + fp32 gradient, both views into per-network flat buffers."""
-    __slots__ = ("name", "data", "grad", "cache", "bf16_ptr")
+    __slots__ = ("name", "data", "grad", "cache", "bf16_ptr", "owner")
 
-    def __init__(self, name, data, grad, bf16_ptr=0):
+    def __init__(self, name, data, grad, bf16_ptr=0, owner=None):
         self.name, self.data, self.grad, self.cache = name, data, grad, {}
         self.bf16_ptr = bf16_ptr  # address of this tensor inside the network's flat bf16 shadow copy (0 = none)
+        self.owner = owner        # ParamTree whose `pack_epoch` says when the fp32 masters may have changed
+
+    @property
+    def epoch(self):
+        return self.owner.pack_epoch if self.owner is not None else 0
 
     @property
     def ptr(self):
@@ -232,11 +237,11 @@ class Ctx:
         Op, Ip = (O + 31) // 32 * 32, (I + 63) // 64 * 64
         key = ("slabs", O, I, wst)
         hit = w.cache.get(key)
-        if hit is None or hit[0] != self.pack_epoch:
+        if hit is None or hit[0] != w.epoch:
             buf = hit[1] if hit is not None else torch.empty(k * k * Op * Ip, dtype=torch.bfloat16, device=self.device)
             self.L.pack_conv_weight(w.ptr, buf.data_ptr(), O, I, Op, Ip, k, k, wst[0], wst[1], wst[2], wst[3], 0,
                                     self.stream)
-            w.cache[key] = hit = (self.pack_epoch, buf)
+            w.cache[key] = hit = (w.epoch, buf)
         return hit[1].data_ptr(), Op, Ip
 
     def _tc_conv(self, geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):

@@ -14,6 +14,7 @@ from .networks import KernelNet
 class Vgg16(KernelNet):
     def __init__(self):
         super().__init__(specs.vgg_spec(with_tail=True))
+        self.frozen_hint = True  # never updated by the step: packed bf16 operands are reused until a tensor is edited
         for name, p in self.named_parameters():
             p.requires_grad = False
             if name.endswith(".bias"):

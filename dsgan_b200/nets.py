@@ -46,6 +46,8 @@ class ParamTree(nn.Module):
         self._flat_grad = None
         self._flat_bf16 = None
         self._plist = None
+        self.pack_epoch = 0      # bumped whenever the bf16 shadows are re-derived
+        self._sig = None         # (tensor versions) at the last refresh; lets frozen networks skip the re-pack
 
     def init_normal(self, gain=0.02):
         """networks.init_weights('normal') (networks.py:49-70): Conv*/Linear weights N(0,gain), biases 0,
@@ -82,16 +84,26 @@ class ParamTree(nn.Module):
             self._flat_bf16 = torch.empty(self._numel, dtype=torch.bfloat16, device=dev)
         if self._plist is None:
             base32, base16 = self._flat.data_ptr(), self._flat_bf16.data_ptr()
-            self._plist = {n: Param(n, p.data, p.grad, base16 + (p.data_ptr() - base32) // 2)
+            self._plist = {n: Param(n, p.data, p.grad, base16 + (p.data_ptr() - base32) // 2, owner=self)
                            for n, p in params.items()}
+            self._sig = None
         return self._flat, self._flat_grad, self._plist
 
     def refresh_bf16(self, ctx):
         """Re-derive the bf16 GEMM operands from the fp32 masters (one pass over the flat buffer).  Called at the
         start of every forward so load_state_dict / in-place edits / optimizer steps can never leave them stale."""
         flat, _g, _p = self.flat_buffers()
+        sig = None
+        if getattr(self, "frozen_hint", False):
+            # network that no optimizer of ours ever touches (VGG, vgg.py:27-28): torch bumps `_version` on every in-place
+            # edit (load_state_dict, .copy_, init); identical versions => identical masters => packed copies still valid.
+            # (NOT keyed on requires_grad: D is frozen in the G step but was just updated by the fused Adam kernel.)
+            sig = tuple(p._version for p in self.parameters())
+            if sig == self._sig:
+                return
+        self._sig = sig
         ctx.L.pack_bf16(flat.data_ptr(), self._flat_bf16.data_ptr(), flat.numel(), ctx.stream)
-        ctx.pack_epoch += 1  # conv-weight slabs cached on the Params are re-packed lazily
+        self.pack_epoch += 1  # conv-weight slabs cached on the Params are re-packed lazily
 
 
 # ------------------------------------------------------------------------------------------------
