@@ -25,8 +25,10 @@ class TcConvDesc(ctypes.Structure):
     """Mirror of dsgan_tc_conv_desc."""
     _fields_ = [(n, ctypes.c_int) for n in
                 ("N", "Hi", "Wi", "Ci", "ld_in", "Ho", "Wo", "Co", "ld_out", "Hg", "Wg", "in_stride", "out_stride",
-                 "oy0", "ox0", "ntaps", "nslabs", "co_pad", "ci_pad")] + \
-               [("dy", ctypes.c_int * 16), ("dx", ctypes.c_int * 16), ("slab", ctypes.c_int * 16)] + \
+                 "nclass")] + \
+               [("oy0", ctypes.c_int * 4), ("ox0", ctypes.c_int * 4), ("ntaps", ctypes.c_int * 4)] + \
+               [(n, ctypes.c_int) for n in ("nslabs", "co_pad", "ci_pad")] + \
+               [("dy", ctypes.c_int * 64), ("dx", ctypes.c_int * 64), ("slab", ctypes.c_int * 64)] + \
                [(n, ctypes.c_int) for n in ("ld_aux", "ld_pre", "act", "dact", "accumulate")]
 
 

@@ -28,10 +28,11 @@ constexpr int TH = 8, TW = 16, BM = TH * TW, BK = 64, EPI_WARPS = 16, NUM_THREAD
 struct ConvParams {
   int N, Hg, Wg;            // images, grid extent (positions per image)
   int Ci, Co, co_pad;
-  int is_, os_, oy0, ox0;   // input stride, output stride, output parity offset
+  int is_, os_;             // input stride, output stride
   int Ho, Wo;               // output extent (pixels)
-  int ntaps;
-  int dy[MAX_TAPS], dx[MAX_TAPS], slab[MAX_TAPS];
+  int nclass;               // output parity classes handled by this launch (1, or 4 for stride-2 transposed ops)
+  int oy0[4], ox0[4], ntaps[4];
+  int dy[4 * MAX_TAPS], dx[4 * MAX_TAPS], slab[4 * MAX_TAPS];
   int tiles_y, tiles_x, n_tiles;
   void* C; int ldc;
   const float* bias;
@@ -69,7 +70,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
-  const int num_tiles = p.N * tiles_per_img * p.n_tiles;
+  const int num_tiles = p.N * tiles_per_img * p.n_tiles * p.nclass;
   const int kc = (p.Ci + BK - 1) / BK;  // channel blocks per tap (TMA zero-fills channels >= Ci)
 
   if (warp == 0 && lane == 0) {
@@ -90,10 +91,11 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = tile % p.n_tiles;
-        const int sp = tile / p.n_tiles;
+        const int cls = (tile / p.n_tiles) % p.nclass;
+        const int sp = tile / (p.n_tiles * p.nclass);
         const int img = sp / tiles_per_img, t2 = sp % tiles_per_img;
         const int y0 = (t2 / p.tiles_x) * TH, x0 = (t2 % p.tiles_x) * TW;
-        for (int t = 0; t < p.ntaps; ++t) {
+        for (int t = cls * MAX_TAPS; t < cls * MAX_TAPS + p.ntaps[cls]; ++t) {
           const int cy = y0 * p.is_ + p.dy[t], cx = x0 * p.is_ + p.dx[t];
           for (int c = 0; c < kc; ++c) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -111,8 +113,8 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       constexpr uint32_t IDESC = idesc_bf16(BM, BN, false, false);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      const int nk = p.ntaps * kc;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nk = p.ntaps[(tile / p.n_tiles) % p.nclass] * kc;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -138,11 +140,12 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_tiles;
-      const int sp = tile / p.n_tiles;
+      const int cls = (tile / p.n_tiles) % p.nclass;
+      const int sp = tile / (p.n_tiles * p.nclass);
       const int img = sp / tiles_per_img, t2 = sp % tiles_per_img;
       const int r = quarter * 32 + lane;
       const int gy = (t2 / p.tiles_x) * TH + r / TW, gx = (t2 % p.tiles_x) * TW + r % TW;
-      const int oy = gy * p.os_ + p.oy0, ox = gx * p.os_ + p.ox0;
+      const int oy = gy * p.os_ + p.oy0[cls], ox = gx * p.os_ + p.ox0[cls];
       const bool row_ok = gy < p.Hg && gx < p.Wg && oy < p.Ho && ox < p.Wo;
       const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
       const bool vec_ok = (p.ldc % 8 == 0) && (!p.aux || p.ld_aux % 8 == 0) && (!p.pre || p.ld_pre % 8 == 0) &&
@@ -456,7 +459,7 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cuda
     if (e != cudaSuccess) { set_error("tc_conv smem attr: %s", cudaGetErrorString(e)); return 1; }
     attr = true;
   }
-  const long long tiles = (long long)p.N * p.tiles_y * p.tiles_x * p.n_tiles;
+  const long long tiles = (long long)p.N * p.tiles_y * p.tiles_x * p.n_tiles * p.nclass;
   const int grid = tiles < sms() ? (int)tiles : sms();
   k_tc_conv<BN><<<grid, NUM_THREADS, smem, s>>>(a, b, p);
   return DS_LAUNCHED("tc_conv");
@@ -501,7 +504,8 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
                   void* pre_out, const void* aux, void* stream) {
   DS_REQUIRE(d && in && w_slabs && out, "tc_conv: null argument");
   DS_REQUIRE(dsgan_tc_conv_supported(d->Ci, d->Co, d->ld_in, d->ld_out), "tc_conv: unsupported Ci=%d Co=%d", d->Ci, d->Co);
-  DS_REQUIRE(d->ntaps >= 1 && d->ntaps <= MAX_TAPS, "tc_conv: ntaps=%d", d->ntaps);
+  DS_REQUIRE(d->nclass >= 1 && d->nclass <= 4, "tc_conv: nclass=%d", d->nclass);
+  for (int c = 0; c < d->nclass; ++c) DS_REQUIRE(d->ntaps[c] >= 1 && d->ntaps[c] <= MAX_TAPS, "tc_conv: ntaps=%d", d->ntaps[c]);
   DS_REQUIRE(d->in_stride == 1 || d->in_stride == 2, "tc_conv: in_stride=%d", d->in_stride);
   DS_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)w_slabs % 16 == 0), "tc_conv: unaligned");
   DS_REQUIRE(d->ci_pad % 64 == 0 && d->ci_pad >= d->Ci && d->co_pad >= d->Co, "tc_conv: bad slab padding");
@@ -513,9 +517,11 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
   ConvParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Ci = d->Ci; p.Co = d->Co; p.co_pad = d->co_pad;
-  p.is_ = d->in_stride; p.os_ = d->out_stride; p.oy0 = d->oy0; p.ox0 = d->ox0; p.Ho = d->Ho; p.Wo = d->Wo;
-  p.ntaps = d->ntaps;
-  for (int t = 0; t < d->ntaps; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.slab[t] = d->slab[t]; }
+  p.is_ = d->in_stride; p.os_ = d->out_stride; p.Ho = d->Ho; p.Wo = d->Wo; p.nclass = d->nclass;
+  for (int c = 0; c < d->nclass; ++c) {
+    p.oy0[c] = d->oy0[c]; p.ox0[c] = d->ox0[c]; p.ntaps[c] = d->ntaps[c];
+    for (int t = c * MAX_TAPS; t < c * MAX_TAPS + d->ntaps[c]; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.slab[t] = d->slab[t]; }
+  }
   p.tiles_y = (d->Hg + TH - 1) / TH; p.tiles_x = (d->Wg + TW - 1) / TW; p.n_tiles = (d->Co + BN - 1) / BN;
   p.C = out; p.ldc = d->ld_out; p.bias = bias; p.pre = pre_out; p.ld_pre = d->ld_pre; p.aux = aux; p.ld_aux = d->ld_aux;
   p.act = d->act; p.dact = d->dact; p.accumulate = d->accumulate;

@@ -272,12 +272,16 @@ class Ctx:
                     taps = [((py + p - ky) // 2, (px + p - kx) // 2, ky * k + kx) for ky in range(k) for kx in range(k)
                             if (py + p - ky) % 2 == 0 and (px + p - kx) % 2 == 0]
                     launches.append(((Ho - py + 1) // 2, (Wo - px + 1) // 2, 1, 2, py, px, taps))
-        for Hg, Wg, is_, os_, oy0, ox0, taps in launches:
-            if not taps or Hg <= 0 or Wg <= 0:
-                continue
-            d.Hg, d.Wg, d.in_stride, d.out_stride, d.oy0, d.ox0, d.ntaps = Hg, Wg, is_, os_, oy0, ox0, len(taps)
-            for i, (dy, dx, sl) in enumerate(taps):
-                d.dy[i], d.dx[i], d.slab[i] = dy, dx, sl
+        launches = [l for l in launches if l[6] and l[0] > 0 and l[1] > 0]
+        # the four output-parity classes of a stride-2 transposed op share one launch when their grids coincide
+        groups = [launches] if len({l[:4] for l in launches}) == 1 else [[l] for l in launches]
+        for grp in groups:
+            Hg, Wg, is_, os_ = grp[0][:4]
+            d.Hg, d.Wg, d.in_stride, d.out_stride, d.nclass = Hg, Wg, is_, os_, len(grp)
+            for c, (_h, _w, _i, _o, oy0, ox0, taps) in enumerate(grp):
+                d.oy0[c], d.ox0[c], d.ntaps[c] = oy0, ox0, len(taps)
+                for i, (dy, dx, sl) in enumerate(taps):
+                    d.dy[16 * c + i], d.dx[16 * c + i], d.slab[16 * c + i] = dy, dx, sl
             self.L.tc_conv(ctypes.byref(d), xin[0], slabs, bias_ptr, out[0], pre[0] if pre else None,
                            aux[0] if aux else None, self.stream)
         return True

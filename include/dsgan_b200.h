@@ -111,7 +111,7 @@ int dsgan_pack_bf16(const float* src, void* dst, long long n, void* stream);
 
 /* tensor-core implicit-GEMM convolution (csrc/tc_conv.cu).  Grid position (y,x) of image n reads input pixel
  * (y*in_stride + dy[t], x*in_stride + dx[t]) for tap t (zero outside the image) against weight slab slab[t], and writes
- * output pixel (y*out_stride + oy0, x*out_stride + ox0).  w_slabs: bf16 [nslabs][co_pad][ci_pad], zero padded
+ * output pixel (y*out_stride + oy0[c], x*out_stride + ox0[c]) of parity class c.  w_slabs: bf16 [nslabs][co_pad][ci_pad], zero padded
  * (dsgan_pack_conv_weight).  Any Ci/Co: the input pixel pitch must be a multiple of 8 elements (TMA zero-fills the
  * channels >= Ci), narrow outputs (Co = 1, 3, 6 ...) take a scalar epilogue.
  * Covers nn.Conv2d s1/s2 and nn.ConvTranspose2d(s2) forward and input-gradients: models/vgg.py:16-25,
@@ -120,10 +120,12 @@ typedef struct {
   int N, Hi, Wi, Ci, ld_in;
   int Ho, Wo, Co, ld_out;
   int Hg, Wg;
-  int in_stride, out_stride, oy0, ox0;
-  int ntaps, nslabs;
+  int in_stride, out_stride;
+  int nclass;         /* 1, or up to 4 output-parity classes handled by one launch (same grid extent for all) */
+  int oy0[4], ox0[4], ntaps[4]; /* per class: output offset and number of taps; taps of class c start at index 16*c */
+  int nslabs;
   int co_pad, ci_pad; /* row / column padding of the packed slabs (>= Co, >= Ci and a multiple of 64) */
-  int dy[16], dx[16], slab[16];
+  int dy[64], dx[64], slab[64];
   int ld_aux, ld_pre, act, dact, accumulate;
 } dsgan_tc_conv_desc;
 int dsgan_tc_conv_supported(int Ci, int Co, int ld_in, int ld_out);

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_mirrors_match_header_sizes():
     # dsgan_conv_desc: 17 ints (+pad) + 4 long long + 3 ints ; dsgan_tc_conv_desc: 19 + 48 + 5 ints
     assert ctypes.sizeof(_lib.ConvDesc) == 120
-    assert ctypes.sizeof(_lib.TcConvDesc) == 4 * (19 + 48 + 5)
+    assert ctypes.sizeof(_lib.TcConvDesc) == 4 * (14 + 12 + 3 + 192 + 5)
     assert ctypes.sizeof(_lib.TcWgradDesc) == 4 * 11 + 4 * 32 + 4 + 8 * 16 + 16
 
 
