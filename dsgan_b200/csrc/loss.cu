@@ -90,7 +90,10 @@ __global__ void k_tv(const float* __restrict__ x, int H, int W, long long total,
   if (threadIdx.x == 0) atomicAdd(loss, acc * inv_denom);
 }
 
+#include "ssim_v2.cuh"
+
 // ---------------------------------------------------------------------------------------------
+// (first-generation kernels, kept as the readable reference of the tiling; the ABI dispatches to ssim_v2.cuh)
 // SSIM forward: 32x32 output tile per block, 42x42 input tiles of X and Y staged in smem.
 constexpr int TS = 32, HALO = 10, TI = TS + HALO;  // 42
 
@@ -346,7 +349,7 @@ int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * NC, s);
   dim3 grid(cdiv(W - HALO, TS), cdiv(H - HALO, TS), NC);
-  k_ssim_fwd<<<grid, 256, 0, s>>>(X, Y, H, W, C1, C2, sums);
+  k_ssim_fwd2<<<grid, 256, 0, s>>>(X, Y, H, W, C1, C2, sums);
   return DS_LAUNCHED("ssim_fwd");
 }
 int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, const float* coef,
@@ -356,12 +359,12 @@ int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C
   if (ensure_window()) return 1;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_ssim_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem));
+    cudaError_t e = cudaFuncSetAttribute(k_ssim_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd2Smem));
     if (e != cudaSuccess) { set_error("ssim_bwd smem attr: %s", cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
   dim3 grid(cdiv(W, TS), cdiv(H, TS), NC);
-  k_ssim_bwd<<<grid, 256, sizeof(BwdSmem), (cudaStream_t)stream>>>(X, Y, H, W, C1, C2, coef, dY, accumulate);
+  k_ssim_bwd2<<<grid, 256, sizeof(Bwd2Smem), (cudaStream_t)stream>>>(X, Y, H, W, C1, C2, coef, dY, accumulate);
   return DS_LAUNCHED("ssim_bwd");
 }
 int dsgan_avgpool2_fwd(const float* x, float* y, int NC, int H, int W, void* stream) {
