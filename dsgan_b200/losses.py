@@ -11,6 +11,35 @@ import torch
 from .engine import ACT_RELU, ACT_SIGMOID, F32, Ctx, Var
 
 MS_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)  # MS_SSIM.py:200
+_CONST = {}   # (device, sizes) -> (1/size per level, weights): built once, so the call never touches the host again
+_WORK = {}    # (device, shape, levels, want_grad) -> reusable pyramid / statistics / gradient workspaces
+
+
+def _consts(device, sizes):
+    key = (str(device), tuple(sizes))
+    if key not in _CONST:
+        _CONST[key] = (torch.tensor([1.0 / s for s in sizes], dtype=torch.float32, device=device),
+                       torch.tensor(MS_WEIGHTS, dtype=torch.float32, device=device))
+    return _CONST[key]
+
+
+def _workspace(X, levels, want):
+    """Pyramid levels, per-plane sums, coefficients and per-level gradient buffers, allocated once per shape (they are
+    fully overwritten by every call)."""
+    N, C, H, W = X.shape
+    key = (str(X.device), N, C, H, W, levels, want)
+    ws = _WORK.get(key)
+    if ws is None:
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=X.device)
+        ws = {"sums": f(levels, N * C, 2), "coef": f(levels, N * C, 2) if want else None, "px": [], "py": [], "g": []}
+        h, w = H, W
+        for lv in range(1, levels):
+            h, w = h // 2, w // 2
+            ws["px"].append(f(N, C, h, w))
+            ws["py"].append(f(N, C, h, w))
+            ws["g"].append(f(N, C, h, w) if want else None)
+        _WORK[key] = ws
+    return ws
 
 
 def gan_loss(ctx: Ctx, pred: Var, target_is_real: bool, slot: int, loss_scale=1.0, grad_scale=1.0, use_lsgan=False,
@@ -74,7 +103,9 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
         raise AssertionError("Image size should be larger than 160 due to the 4 downsamplings in ms-ssim")
     if min(H, W) < 11:
         raise ValueError("ssim needs H, W >= 11 (win_size), got %dx%d" % (H, W))
-    sums = per_plane if per_plane is not None else ctx.f32(levels, NC, 2)
+    want = dY is not None
+    ws = _workspace(X, levels, want)
+    sums = per_plane if per_plane is not None else ws["sums"]
     xs, ys, sizes = [X], [Y], []
     for lv in range(levels):
         h, w = xs[lv].shape[-2:]
@@ -83,17 +114,14 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
         if lv < levels - 1:
             if h % 2 or w % 2:
                 raise ValueError("ms_ssim: odd pyramid level %dx%d is not supported" % (h, w))
-            nx = torch.empty((N, C, h // 2, w // 2), dtype=torch.float32, device=X.device)
-            ny = torch.empty_like(nx)
+            nx, ny = ws["px"][lv], ws["py"][lv]
             L_.avgpool2_fwd(xs[lv].data_ptr(), nx.data_ptr(), NC, h, w, ctx.stream)
             L_.avgpool2_fwd(ys[lv].data_ptr(), ny.data_ptr(), NC, h, w, ctx.stream)
             xs.append(nx)
             ys.append(ny)
-    want = dY is not None
-    coef = ctx.f32(levels, NC, 2) if want else None
+    coef = ws["coef"]
     if multiscale:
-        inv = torch.tensor([1.0 / s for s in sizes], dtype=torch.float32).to(X.device, non_blocking=True)
-        wts = torch.tensor(MS_WEIGHTS, dtype=torch.float32).to(X.device, non_blocking=True)
+        inv, wts = _consts(X.device, sizes)
         L_.msssim_combine(sums.data_ptr(), inv.data_ptr(), wts.data_ptr(), levels, NC, out_scale, slot, grad_scale,
                           coef.data_ptr() if want else None, ctx.stream)
     else:
@@ -105,7 +133,7 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
     g_next = None
     for lv in reversed(range(levels)):
         h, w = xs[lv].shape[-2:]
-        g = dY if lv == 0 else torch.empty_like(ys[lv])
+        g = dY if lv == 0 else ws["g"][lv - 1]
         L_.ssim_bwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, coef[lv].data_ptr(), g.data_ptr(),
                     1 if lv == 0 else 0, ctx.stream)
         if g_next is not None:
