@@ -24,7 +24,7 @@ __device__ __forceinline__ void ld14x2(const float2* p, float2 (&v)[14]) {
 constexpr int VF_IN = V_TS + V_HALO;  // 42 input rows / cols
 constexpr int VF_P = 44;              // padded pitch (16-byte aligned rows, readable up to column 43)
 
-__global__ void __launch_bounds__(256) k_ssim_fwd2(const float* __restrict__ X, const float* __restrict__ Y, int H, int W,
+__global__ void __launch_bounds__(256, 4) k_ssim_fwd2(const float* __restrict__ X, const float* __restrict__ Y, int H, int W,
                                                     float C1, float C2, float* __restrict__ sums) {
   __shared__ __align__(16) float sX[VF_IN][VF_P], sY[VF_IN][VF_P];
   __shared__ __align__(16) float2 sM[VF_IN][V_TS], sQ[VF_IN][V_TS];  // (mu1, mu2), (E xx, E yy) after the horizontal pass
