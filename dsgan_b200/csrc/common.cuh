@@ -96,6 +96,16 @@ __device__ __forceinline__ void gelu_parts_fast2(float2 x, float2& cdf, float2& 
   cdf = __ffma2_rn(make_float2(0.5f, 0.5f), erfz, make_float2(0.5f, 0.5f));
   pdf = __fmul2_rn(make_float2(0.39894228040143268f, 0.39894228040143268f), e);
 }
+__device__ __forceinline__ float2 act_fwd_fast2(int act, float2 u) {
+  if (act == ACT_GELU) { float2 c, p; gelu_parts_fast2(u, c, p); return __fmul2_rn(u, c); }
+  if (act == ACT_NONE) return u;
+  return make_float2(act_fwd(act, u.x), act_fwd(act, u.y));
+}
+__device__ __forceinline__ float2 act_bwd_fast2(int act, float2 u) {
+  if (act == ACT_GELU) { float2 c, p; gelu_parts_fast2(u, c, p); return __ffma2_rn(u, p, c); }
+  if (act == ACT_NONE) return make_float2(1.f, 1.f);
+  return make_float2(act_bwd(act, u.x), act_bwd(act, u.y));
+}
 // v[0..n) <- act(v) / v *= act'(a), two at a time for GELU
 template <int N>
 __device__ __forceinline__ void act_fwd_fast_vec(int act, float (&v)[N]) {

@@ -212,6 +212,23 @@ __global__ void __launch_bounds__(256) k_in_stats_v8(const bf16* __restrict__ x,
   }
 }
 
+__device__ __forceinline__ float2 bf2(uint32_t w) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w)); }
+__device__ __forceinline__ uint32_t f2b(float2 v) {
+  __nv_bfloat162 h = __float22bfloat162_rn(v);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// per-thread normalisation constants of its 8 channels as 4 float2 pairs: xhat = x * rstd + shift, shift = -mean * rstd
+__device__ __forceinline__ void norm_consts(const float* stats, int n, int C, int c0, float inv, float2 (&rs)[4], float2 (&sh)[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float m0, r0, m1, r1;
+    mean_rstd(stats + ((size_t)n * C + c0 + 2 * e) * 3, inv, m0, r0);
+    mean_rstd(stats + ((size_t)n * C + c0 + 2 * e + 1) * 3, inv, m1, r1);
+    rs[e] = make_float2(r0, r1);
+    sh[e] = make_float2(-m0 * r0, -m1 * r1);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x, int ldx, const float* __restrict__ stats,
                                                       const bf16* __restrict__ res, int ldr, bf16* __restrict__ y, int ldy,
                                                       long long HW, int C, int act, int VCHUNK) {
@@ -222,22 +239,22 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
   const size_t base = (size_t)n * HW;
   const float inv = 1.0f / (float)HW;
   for (int c0 = blockIdx.z * l.gl * 8 + l.tg * 8; c0 < min(C, (int)(blockIdx.z + 1) * l.gl * 8); c0 += l.gl * 8) {
-    float mean[8], rstd[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]);
+    float2 rs[4], sh[4];
+    norm_consts(stats, n, C, c0, inv, rs, sh);
 #pragma unroll 4
     for (long long p = p0 + l.tp; p < p1; p += l.pl) {
-      float v[8], r[8];
-      unpack8(ld8(x + (base + p) * ldx + c0), v);
-      if (res) unpack8(ld8(res + (base + p) * ldr + c0), r);
+      const uint4 xv = ld8(x + (base + p) * ldx + c0);
+      uint4 rv = make_uint4(0, 0, 0, 0);
+      if (res) rv = ld8(res + (base + p) * ldr + c0);
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+      uint32_t ow[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float u = (v[e] - mean[e]) * rstd[e];
-        if (res) u += r[e];
-        v[e] = u;
+      for (int e = 0; e < 4; ++e) {
+        float2 u = __ffma2_rn(bf2(xw[e]), rs[e], sh[e]);
+        if (res) u = __fadd2_rn(u, bf2(rw[e]));
+        ow[e] = f2b(act_fwd_fast2(act, u));
       }
-      act_fwd_fast_vec<8>(act, v);
-      *reinterpret_cast<uint4*>(y + (base + p) * ldy + c0) = pack8(v);
+      *reinterpret_cast<uint4*>(y + (base + p) * ldy + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
 }
@@ -258,22 +275,28 @@ __global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict_
     __syncthreads();
     const int c0 = cb + l.tg * 8;
     if (l.tp < l.pl && c0 < C) {
-      float mean[8], rstd[8], sg[8], sgx[8];
+      float2 rs[4], sh[4], sg2[4], sgx2[4];
+      norm_consts(stats, n, C, c0, inv, rs, sh);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]); sg[e] = sgx[e] = 0.f; }
+      for (int e = 0; e < 4; ++e) sg2[e] = sgx2[e] = make_float2(0.f, 0.f);
 #pragma unroll 4
       for (long long p = p0 + l.tp; p < p1; p += l.pl) {
-        float v[8], g[8], r[8];
-        unpack8(ld8(x + (base + p) * ldx + c0), v);
-        unpack8(ld8(dy + (base + p) * lddy + c0), g);
-        if (act && res) unpack8(ld8(res + (base + p) * ldr + c0), r);
-        float xh[8], u[8];
+        const uint4 xv = ld8(x + (base + p) * ldx + c0), gv = ld8(dy + (base + p) * lddy + c0);
+        uint4 rv = make_uint4(0, 0, 0, 0);
+        if (act && res) rv = ld8(res + (base + p) * ldr + c0);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { xh[e] = (v[e] - mean[e]) * rstd[e]; u[e] = res ? xh[e] + r[e] : xh[e]; }
-        act_bwd_fast_mul<8>(act, g, u);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { sg[e] += g[e]; sgx[e] = fmaf(g[e], xh[e], sgx[e]); }
+        for (int e = 0; e < 4; ++e) {
+          const float2 xh = __ffma2_rn(bf2(xw[e]), rs[e], sh[e]);
+          float2 g = bf2(gw[e]);
+          if (act) g = __fmul2_rn(g, act_bwd_fast2(act, res ? __fadd2_rn(xh, bf2(rw[e])) : xh));
+          sg2[e] = __fadd2_rn(sg2[e], g);
+          sgx2[e] = __ffma2_rn(g, xh, sgx2[e]);
+        }
       }
+      float sg[8], sgx[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { sg[2 * e] = sg2[e].x; sg[2 * e + 1] = sg2[e].y; sgx[2 * e] = sgx2[e].x; sgx[2 * e + 1] = sgx2[e].y; }
 #pragma unroll
       for (int e = 0; e < 8; ++e) { atomicAdd(&sacc[0][l.tg * 8 + e], sg[e]); atomicAdd(&sacc[1][l.tg * 8 + e], sgx[e]); }
     }
@@ -301,42 +324,46 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
   const size_t base = (size_t)n * HW;
   const float inv = 1.0f / (float)HW;
   for (int c0 = blockIdx.z * l.gl * 8 + l.tg * 8; c0 < min(C, (int)(blockIdx.z + 1) * l.gl * 8); c0 += l.gl * 8) {
-    float mean[8], rstd[8], mg[8], mgx[8];
+    float2 rs[4], sh[4], mg[4], mgx[4];
+    norm_consts(stats, n, C, c0, inv, rs, sh);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      mean_rstd(stats + ((size_t)n * C + c0 + e) * 3, inv, mean[e], rstd[e]);
-      mg[e] = bst[((size_t)n * C + c0 + e) * 2] * inv;
-      mgx[e] = bst[((size_t)n * C + c0 + e) * 2 + 1] * inv;
+    for (int e = 0; e < 4; ++e) {
+      const float* b0 = bst + ((size_t)n * C + c0 + 2 * e) * 2;
+      mg[e] = make_float2(b0[0] * inv, b0[2] * inv);
+      mgx[e] = make_float2(-b0[1] * inv, -b0[3] * inv);  // negated: t = g - mg + xh * (-mgx)
     }
 #pragma unroll 2
     for (long long p = p0 + l.tp; p < p1; p += l.pl) {
-      float v[8], g[8], r[8], o[8];
-      unpack8(ld8(x + (base + p) * ldx + c0), v);
-      unpack8(ld8(dy + (base + p) * lddy + c0), g);
-      if (act && res) unpack8(ld8(res + (base + p) * ldr + c0), r);
-      float xh[8], u[8];
+      const uint4 xv = ld8(x + (base + p) * ldx + c0), gv = ld8(dy + (base + p) * lddy + c0);
+      uint4 rv = make_uint4(0, 0, 0, 0);
+      if (act && res) rv = ld8(res + (base + p) * ldr + c0);
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+      float2 g[4], o[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { xh[e] = (v[e] - mean[e]) * rstd[e]; u[e] = res ? xh[e] + r[e] : xh[e]; }
-      act_bwd_fast_mul<8>(act, g, u);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = rstd[e] * (g[e] - mg[e] - xh[e] * mgx[e]);
+      for (int e = 0; e < 4; ++e) {
+        const float2 xh = __ffma2_rn(bf2(xw[e]), rs[e], sh[e]);
+        g[e] = bf2(gw[e]);
+        if (act) g[e] = __fmul2_rn(g[e], act_bwd_fast2(act, res ? __fadd2_rn(xh, bf2(rw[e])) : xh));
+        const float2 t = __ffma2_rn(xh, mgx[e], __fadd2_rn(g[e], make_float2(-mg[e].x, -mg[e].y)));
+        o[e] = __fmul2_rn(rs[e], t);
+      }
       uint4* dp = reinterpret_cast<uint4*>(dx + (base + p) * lddx + c0);
       if (acc_dx) {
-        float old[8];
-        unpack8(*dp, old);
+        const uint4 ov = *dp;
+        const uint32_t owd[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] += old[e];
+        for (int e = 0; e < 4; ++e) o[e] = __fadd2_rn(o[e], bf2(owd[e]));
       }
-      *dp = pack8(o);
+      *dp = make_uint4(f2b(o[0]), f2b(o[1]), f2b(o[2]), f2b(o[3]));
       if (dres) {
         uint4* rp = reinterpret_cast<uint4*>(dres + (base + p) * lddr + c0);
         if (acc_dres) {
-          float old[8];
-          unpack8(*rp, old);
+          const uint4 ov = *rp;
+          const uint32_t owd[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) g[e] += old[e];
+          for (int e = 0; e < 4; ++e) g[e] = __fadd2_rn(g[e], bf2(owd[e]));
         }
-        *rp = pack8(g);
+        *rp = make_uint4(f2b(g[0]), f2b(g[1]), f2b(g[2]), f2b(g[3]));
       }
     }
   }
