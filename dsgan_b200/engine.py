@@ -143,6 +143,29 @@ class Profile:
         return out
 
 
+class _NoFork:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class _Fork:
+    def __init__(self, ctx, side, main):
+        self.ctx, self.side, self.main = ctx, side, main
+
+    def __enter__(self):
+        self._cm = torch.cuda.stream(self.side)
+        self._cm.__enter__()
+        self._prev, self.ctx._side = self.ctx._side, self.side
+        return self
+
+    def __exit__(self, *a):
+        self.ctx._side = self._prev
+        return self._cm.__exit__(*a)
+
+
 class Ctx:
     """One engine context per device: dtype mode, tape, scratch, kernel wrappers."""
 
@@ -158,6 +181,8 @@ class Ctx:
         self.param_grads = True   # False while D is frozen in the G step (pix2pix_model.py:214)
         self.no_grad = False
         self.use_tc = True        # bf16 mode: route eligible GEMMs to the tcgen05 kernels
+        self.use_streams = True   # run independent branches on a side stream (fork/join)
+        self._side, self._side_stream = None, None
         self.pack_epoch = 0       # bumped whenever a network's fp32 masters may have changed (ParamTree.refresh_bf16)
 
     @property
@@ -201,14 +226,57 @@ class Ctx:
 
     def record(self, fn):
         if not self.no_grad:
-            self.tape.append(fn)
+            self.tape.append(fn if self._side is None else (fn, self._side))
+
+    # ---- stream-level concurrency -----------------------------------------------------------------------------------
+    # Independent sub-graphs (the OriginMLKA branch next to the main U-Net, D(fake) next to D(real)) are made of many
+    # 10-40 us kernels that cannot fill 148 SMs on their own.  fork()/join() put such a branch on a side stream; the
+    # same markers replayed in reverse give the backward pass the mirrored concurrency.
+    def fork(self):
+        """-> context manager: everything launched (and recorded) inside runs on a side stream that first waits for
+        the work already queued on the current stream."""
+        if not self.use_streams:
+            return _NoFork()
+        main = torch.cuda.current_stream(self.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+        side = self._side_stream
+        side.wait_stream(main)
+        if not self.no_grad:
+            self.tape.append(("fork", side, main, []))
+        return _Fork(self, side, main)
+
+    def join(self, fk, keep=()):
+        """Make the current stream wait for the forked branch.  `keep`: Vars that cross the two streams; they are held
+        until the mirrored join of the backward pass so the caching allocator cannot hand their memory to one stream
+        while the other still uses it."""
+        if isinstance(fk, _NoFork):
+            return
+        fk.main.wait_stream(fk.side)
+        if not self.no_grad:
+            self.tape.append(("join", fk.side, fk.main, list(keep)))
 
     def backward(self, tape=None):
         """Run (and drop) a tape in reverse; default: the context's current tape."""
         if tape is None:
             tape, self.tape = self.tape, []
+        held = []
         while tape:  # popping lets each layer's activations and gradients be freed as soon as it is done
-            tape.pop()()
+            item = tape.pop()
+            if not isinstance(item, tuple):
+                item()
+            elif item[0] == "join":     # forward join == backward fork: the side branch may start once we got here
+                _kind, side, main, keep = item
+                side.wait_stream(main)
+                held.append(keep)
+            elif item[0] == "fork":     # forward fork == backward join
+                _kind, side, main, _keep = item
+                main.wait_stream(side)
+                held.clear()
+            else:
+                fn, side = item
+                with torch.cuda.stream(side):
+                    fn()
 
     def take_tape(self):
         """Detach the recorded tape (e.g. keep G's graph alive across the D step)."""
@@ -237,11 +305,18 @@ class Ctx:
         Op, Ip = (O + 31) // 32 * 32, (I + 63) // 64 * 64
         key = ("slabs", O, I, wst)
         hit = w.cache.get(key)
+        cur = torch.cuda.current_stream(self.device)
         if hit is None or hit[0] != w.epoch:
             buf = hit[1] if hit is not None else torch.empty(k * k * Op * Ip, dtype=torch.bfloat16, device=self.device)
+            if hit is not None:
+                cur.wait_event(hit[2])  # a re-pack must not overtake readers of the previous contents on another stream
             self.L.pack_conv_weight(w.ptr, buf.data_ptr(), O, I, Op, Ip, k, k, wst[0], wst[1], wst[2], wst[3], 0,
                                     self.stream)
-            w.cache[key] = hit = (w.epoch, buf)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            w.cache[key] = hit = (w.epoch, buf, ev, cur)
+        elif hit[3] != cur:
+            cur.wait_event(hit[2])      # packed on another stream (forked branch sharing the same weights)
         return hit[1].data_ptr(), Op, Ip
 
     def _tc_conv(self, geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):

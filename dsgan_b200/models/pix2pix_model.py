@@ -9,7 +9,7 @@ so its gradient is pre-scaled by `world` to keep R-rank training equal to single
 """
 import torch
 
-from .. import losses, parallel
+from .. import losses, nets, parallel
 from ..engine import image_to_nhwc, nhwc_grad_to_image
 from ..optim import FlatAdam
 from ..util.image_pool import ImagePool
@@ -99,10 +99,14 @@ class Pix2PixModel(BaseModel):
             xr = self._pair(self.real_A, self.real_B)
         else:
             xf, xr = image_to_nhwc(ctx, self.fake_B), image_to_nhwc(ctx, self.real_B)
-        pred_fake = self.netD.forward_var(xf, need_dx=False)
-        losses.gan_loss(ctx, pred_fake, False, self._slot("D_fake"), 1.0, 0.5, **self._gan_kw())
-        pred_real = self.netD.forward_var(xr, need_dx=False)
+        P = self.netD.params()  # (refreshes the bf16 operands once, before the two branches fork)
+        fk = ctx.fork()         # D(fake) and D(real) are independent: run them on two streams
+        with fk:
+            pred_fake = nets.discriminator_forward(ctx, P, xf, need_dx=False)
+            losses.gan_loss(ctx, pred_fake, False, self._slot("D_fake"), 1.0, 0.5, **self._gan_kw())
+        pred_real = nets.discriminator_forward(ctx, P, xr, need_dx=False)
         losses.gan_loss(ctx, pred_real, True, self._slot("D_real"), 1.0, 0.5, **self._gan_kw())
+        ctx.join(fk, keep=(xf, xr, pred_fake))
         ctx.backward()  # loss_D = 0.5*(fake+real)
 
     def backward_G(self):

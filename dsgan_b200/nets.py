@@ -170,6 +170,9 @@ def generator_forward(ctx: Ctx, P, x: Var) -> Var:
     """MixConvNeXtML.forward (MixConvNeXtML.py:461-494) -> NHWC 3-channel output Var."""
     if x.H % 16 or x.W % 16:
         raise ValueError("MixConvNeXtML needs H and W to be multiples of 16, got %dx%d" % (x.H, x.W))
+    fk = ctx.fork()          # the local (OriginMLKA) branch only shares the input with the main U-Net
+    with fk:
+        loc = _local(ctx, P, x)
     R, t = [], x
     for i, (name, _cin, _cout) in enumerate(specs.ENC):
         t = _block(ctx, P, name, t if i == 0 else maxpool(ctx, t, 2), need_dx=i > 0)
@@ -186,7 +189,7 @@ def generator_forward(ctx: Ctx, P, x: Var) -> Var:
         o = _block(ctx, P, blk, _upsample(ctx, P, up + ".model.0", o, skip))
         if s is not None:
             o = add_n(ctx, [o] + lvl[s])
-    loc = _local(ctx, P, x)
+    ctx.join(fk, keep=(x, loc))
     return conv2d(ctx, add_n(ctx, [o, loc]), P["res.weight"], P["res.bias"], 3, pad=1)
 
 
