@@ -201,36 +201,48 @@ __global__ void k_colsum(const T* __restrict__ x, int ld, long long npix, int C,
   }
 }
 
-// bf16 fast path of colsum: 8 channels per thread, smem reduction, one global atomic per (block, channel)
+// bf16 fast path of colsum: 8 channels (16 B) per thread, 4 independent row loads in flight per thread, smem
+// reduction over the block's pixel lanes, one global atomic per (block, channel).  grid = (pixel chunks, channel blocks).
 __global__ void __launch_bounds__(256) k_colsum_v8(const bf16* __restrict__ x, int ld, long long npix, int C,
                                                     float* __restrict__ out, long long chunk) {
   __shared__ float sacc[256];
   const int groups = C / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;
   const int tg = threadIdx.x % gl, tp = threadIdx.x / gl;
   const long long p0 = (long long)blockIdx.x * chunk, p1 = min(p0 + chunk, npix);
-  for (int cb = 0; cb < C; cb += gl * 8) {
-    sacc[threadIdx.x] = 0.f;
-    __syncthreads();
-    const int c0 = cb + tg * 8;
-    if (tp < pl && c0 < C) {
-      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (long long p = p0 + tp; p < p1; p += pl) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + p * ld + c0));
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  const int cb = blockIdx.y * gl * 8, c0 = cb + tg * 8;
+  sacc[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (tp < pl && c0 < C) {
+    float2 a[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    const bf16* xp = x + c0;
+    long long p = p0 + tp;
+    for (; p + 3 * pl < p1; p += 4 * pl) {
+      uint4 u[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-          a[2 * e] += __low2float(h);
-          a[2 * e + 1] += __high2float(h);
-        }
+      for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(xp + (p + (long long)j * pl) * ld));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          a[e] = __fadd2_rn(a[e], __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e])));
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&sacc[tg * 8 + e], a[e]);
     }
-    __syncthreads();
-    if (threadIdx.x < gl * 8 && cb + threadIdx.x < C) atomicAdd(out + cb + threadIdx.x, sacc[threadIdx.x]);
-    __syncthreads();
+    for (; p < p1; p += pl) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xp + p * ld));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        a[e] = __fadd2_rn(a[e], __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e])));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(&sacc[tg * 8 + 2 * e], a[e].x);
+      atomicAdd(&sacc[tg * 8 + 2 * e + 1], a[e].y);
+    }
   }
+  __syncthreads();
+  if (threadIdx.x < gl * 8 && cb + threadIdx.x < C) atomicAdd(out + cb + threadIdx.x, sacc[threadIdx.x]);
 }
 }  // namespace
 
@@ -271,13 +283,21 @@ int dsgan_conv_wgrad(const dsgan_conv_desc* d, const void* in, const void* dout,
 }
 
 int dsgan_colsum(const void* x, int dtype, int ld, long long npix, int C, float* out, void* stream) {
+  if (dtype == DT_BF16 && C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16 == 0)) {
+    const int groups = C / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;
+    const int cblocks = (C + gl * 8 - 1) / (gl * 8);
+    // ~8 CTAs per SM over the whole launch, at least 16 rows per pixel lane so the 4-deep unroll is used
+    long long blocks = (148 * 8 + cblocks - 1) / cblocks;
+    long long chunk = (npix + blocks - 1) / blocks;
+    if (chunk < 16LL * pl) chunk = 16LL * pl;
+    blocks = (npix + chunk - 1) / chunk;
+    dim3 grid((unsigned)blocks, (unsigned)cblocks);
+    k_colsum_v8<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, npix, C, out, chunk);
+    return DS_LAUNCHED("colsum_v8");
+  }
   long long chunk = 1024;
   long long blocks = (npix + chunk - 1) / chunk;
   if (blocks > 148 * 8) { chunk = (npix + 148 * 8 - 1) / (148 * 8); blocks = (npix + chunk - 1) / chunk; }
-  if (dtype == DT_BF16 && C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16 == 0)) {
-    k_colsum_v8<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, npix, C, out, chunk);
-    return DS_LAUNCHED("colsum_v8");
-  }
   DS_DISPATCH_DT(dtype, (k_colsum<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, npix, C,
                                                                                         out, chunk)));
   return DS_LAUNCHED("colsum");

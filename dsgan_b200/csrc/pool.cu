@@ -78,72 +78,140 @@ __device__ __forceinline__ uint4 pack8p(const float (&f)[8]) {
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
-__global__ void k_maxpool_fwd_v8(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy, int H, int W, int C,
-                                 int k, long long total) {
+// K = window (2/4/8/16): the window is scanned in row batches of UB = min(K, 8) independent 16-byte loads
+template <int K>
+__global__ void __launch_bounds__(256) k_maxpool_fwd_v8(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+                                                         int H, int W, int C, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int G = C / 8, Ho = H / k, Wo = W / k;
+  constexpr int UB = K < 8 ? K : 8;
+  const int G = C / 8, Ho = H / K, Wo = W / K;
   const int c0 = (int)(i % G) * 8;
   const long long op = i / G;
   const int ox = (int)(op % Wo);
   const long long r = op / Wo;
   const int oy = (int)(r % Ho);
   const long long n = r / Ho;
-  const bf16* xb = x + ((n * H + (long long)oy * k) * W + (long long)ox * k) * ldx + c0;
+  const bf16* xb = x + ((n * H + (long long)oy * K) * W + (long long)ox * K) * ldx + c0;
   float m[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
-  for (int ky = 0; ky < k; ++ky)
-    for (int kx = 0; kx < k; ++kx) {
-      float v[8];
-      unpack8p(__ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kx) * ldx)), v);
+#pragma unroll(K <= 4 ? K : 1)
+  for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+    for (int kb = 0; kb < K; kb += UB) {
+      uint4 u[UB];
+#pragma unroll
+      for (int j = 0; j < UB; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kb + j) * ldx));
+#pragma unroll
+      for (int j = 0; j < UB; ++j) {
+        float v[8];
+        unpack8p(u[j], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
     }
   *reinterpret_cast<uint4*>(y + op * ldy + c0) = pack8p(m);
 }
-__global__ void k_maxpool_bwd_v8(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy, int lddy,
-                                 bf16* __restrict__ dx, int lddx, int H, int W, int C, int k, int acc, int relu_mask,
-                                 long long total) {
+
+template <int K>
+__global__ void __launch_bounds__(256) k_maxpool_bwd_v8(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
+                                                         int lddy, bf16* __restrict__ dx, int lddx, int H, int W, int C,
+                                                         int acc, int relu_mask, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int G = C / 8, Ho = H / k, Wo = W / k;
+  constexpr int UB = K < 8 ? K : 8;
+  const int G = C / 8, Ho = H / K, Wo = W / K;
   const int c0 = (int)(i % G) * 8;
   const long long op = i / G;
   const int ox = (int)(op % Wo);
   const long long r = op / Wo;
   const int oy = (int)(r % Ho);
   const long long n = r / Ho;
-  const long long win = (n * H + (long long)oy * k) * W + (long long)ox * k;
+  const long long win = (n * H + (long long)oy * K) * W + (long long)ox * K;
   const bf16* xb = x + win * ldx + c0;
+  bf16* db = dx + win * lddx + c0;
+  const uint4 gu = __ldg(reinterpret_cast<const uint4*>(dy + op * lddy + c0));
   float m[8];
   int am[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; am[e] = 0; }
-  for (int ky = 0; ky < k; ++ky)
-    for (int kx = 0; kx < k; ++kx) {
-      float v[8];
-      unpack8p(__ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kx) * ldx)), v);
+  if constexpr (K == 2) {
+    // whole window (and the accumulate operand) in registers: 4 + 4 independent loads, then 4 stores
+    uint4 xu[4], ou[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xu[t] = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)(t >> 1) * W + (t & 1)) * ldx));
+    if (acc) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) ou[t] = *reinterpret_cast<const uint4*>(db + ((long long)(t >> 1) * W + (t & 1)) * lddx);
+    }
+    float xv[4][8], g[8];
+    unpack8p(gu, g);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      unpack8p(xu[t], xv[t]);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        if (v[e] > m[e]) { m[e] = v[e]; am[e] = ky * k + kx; }
+        if (xv[t][e] > m[e]) { m[e] = xv[t][e]; am[e] = t; }  // strict: first maximum in scan order (Q5)
     }
-  float g[8];
-  unpack8p(__ldg(reinterpret_cast<const uint4*>(dy + op * lddy + c0)), g);
-  bf16* db = dx + win * lddx + c0;
-  for (int ky = 0; ky < k; ++ky)
-    for (int kx = 0; kx < k; ++kx) {
-      uint4* o = reinterpret_cast<uint4*>(db + ((long long)ky * W + kx) * lddx);
-      float v[8], old[8], xv[8];
-      if (acc) unpack8p(*o, old);
-      if (relu_mask) unpack8p(__ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kx) * ldx)), xv);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float v[8], old[8];
+      if (acc) unpack8p(ou[t], old);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        v[e] = (am[e] == ky * k + kx) ? g[e] : 0.f;
+        v[e] = (am[e] == t) ? g[e] : 0.f;
         if (acc) v[e] += old[e];
-        if (relu_mask && !(xv[e] > 0.f)) v[e] = 0.f;
+        if (relu_mask && !(xv[t][e] > 0.f)) v[e] = 0.f;
       }
-      *o = pack8p(v);
+      *reinterpret_cast<uint4*>(db + ((long long)(t >> 1) * W + (t & 1)) * lddx) = pack8p(v);
+    }
+    return;
+  }
+#pragma unroll(K <= 4 ? K : 1)
+  for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+    for (int kb = 0; kb < K; kb += UB) {
+      uint4 u[UB];
+#pragma unroll
+      for (int j = 0; j < UB; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kb + j) * ldx));
+#pragma unroll
+      for (int j = 0; j < UB; ++j) {
+        float v[8];
+        unpack8p(u[j], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (v[e] > m[e]) { m[e] = v[e]; am[e] = ky * K + kb + j; }
+      }
+    }
+  float g[8];
+  unpack8p(gu, g);
+#pragma unroll(K <= 4 ? K : 1)
+  for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+    for (int kb = 0; kb < K; kb += UB) {
+      uint4 ou[UB], xu[UB];
+      if (acc) {
+#pragma unroll
+        for (int j = 0; j < UB; ++j) ou[j] = *reinterpret_cast<const uint4*>(db + ((long long)ky * W + kb + j) * lddx);
+      }
+      if (relu_mask) {
+#pragma unroll
+        for (int j = 0; j < UB; ++j) xu[j] = __ldg(reinterpret_cast<const uint4*>(xb + ((long long)ky * W + kb + j) * ldx));
+      }
+#pragma unroll
+      for (int j = 0; j < UB; ++j) {
+        float v[8], old[8], xv[8];
+        if (acc) unpack8p(ou[j], old);
+        if (relu_mask) unpack8p(xu[j], xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v[e] = (am[e] == ky * K + kb + j) ? g[e] : 0.f;
+          if (acc) v[e] += old[e];
+          if (relu_mask && !(xv[e] > 0.f)) v[e] = 0.f;
+        }
+        *reinterpret_cast<uint4*>(db + ((long long)ky * W + kb + j) * lddx) = pack8p(v);
+      }
     }
 }
 
@@ -275,9 +343,12 @@ int dsgan_maxpool_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int
                       void* stream) {
   DS_REQUIRE(k >= 1 && H % k == 0 && W % k == 0, "maxpool: H,W (%d,%d) must be multiples of k=%d", H, W, k);
   const long long total = (long long)N * (H / k) * (W / k) * C;
-  if (dtype == DT_BF16 && C % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
-    k_maxpool_fwd_v8<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C,
-                                                                            k, total / 8);
+  if (dtype == DT_BF16 && (k == 2 || k == 4 || k == 8 || k == 16) && C % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 &&
+      (uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0) {
+#define DS_MP_FWD(K) k_maxpool_fwd_v8<K><<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>( \
+    (const bf16*)x, ld_x, (bf16*)y, ld_y, H, W, C, total / 8)
+    if (k == 2) DS_MP_FWD(2); else if (k == 4) DS_MP_FWD(4); else if (k == 8) DS_MP_FWD(8); else DS_MP_FWD(16);
+#undef DS_MP_FWD
     return DS_LAUNCHED("maxpool_fwd_v8");
   }
   DS_DISPATCH_DT(dtype, (k_maxpool_fwd<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld_x, (T*)y,
@@ -288,10 +359,13 @@ int dsgan_maxpool_bwd(const void* x, int ld_x, const void* dy, int ld_dy, void* 
                       int W, int C, int k, int accumulate, int relu_mask, void* stream) {
   DS_REQUIRE(k >= 1 && H % k == 0 && W % k == 0, "maxpool: H,W (%d,%d) must be multiples of k=%d", H, W, k);
   const long long total = (long long)N * (H / k) * (W / k) * C;
-  if (dtype == DT_BF16 && C % 8 == 0 && ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && (uintptr_t)x % 16 == 0 &&
+  if (dtype == DT_BF16 && (k == 2 || k == 4 || k == 8 || k == 16) && C % 8 == 0 && ld_x % 8 == 0 && ld_dy % 8 == 0 &&
+      ld_dx % 8 == 0 && (uintptr_t)x % 16 == 0 &&
       (uintptr_t)dy % 16 == 0 && (uintptr_t)dx % 16 == 0) {
-    k_maxpool_bwd_v8<<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (bf16*)dx, ld_dx, H, W, C, k, accumulate, relu_mask, total / 8);
+#define DS_MP_BWD(K) k_maxpool_bwd_v8<K><<<cdiv(total / 8, 256), 256, 0, (cudaStream_t)stream>>>( \
+    (const bf16*)x, ld_x, (const bf16*)dy, ld_dy, (bf16*)dx, ld_dx, H, W, C, accumulate, relu_mask, total / 8)
+    if (k == 2) DS_MP_BWD(2); else if (k == 4) DS_MP_BWD(4); else if (k == 8) DS_MP_BWD(8); else DS_MP_BWD(16);
+#undef DS_MP_BWD
     return DS_LAUNCHED("maxpool_bwd_v8");
   }
   DS_DISPATCH_DT(dtype, (k_maxpool_bwd<T><<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
