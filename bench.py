@@ -191,9 +191,13 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel family (dense conv / GEMM), timed live with CUDA events ----
     ctx = model.ctx
+    # (one extra step with every launch bracketed by CUDA events on its stream; the side stream is disabled for it so that
+    # each kernel is timed alone instead of sharing the SMs with the concurrent branch)
     ctx.profile = engine.Profile()
+    streams, ctx.use_streams = ctx.use_streams, False
     model.optimize_parameters()
     torch.cuda.synchronize()
+    ctx.use_streams = streams
     prof = ctx.profile.summary()
     if rank == 0 and args.detail:
         for ms_, n_, tf_, name_ in ctx.profile.detail(400):

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) k_dwconv_t(const bf16* __restrict__ x, in
   const int gy = y0 + row;
   if (gy >= H) return;
   const int c0 = c_base + pair * 2;
-  const float b0 = bias ? __ldg(bias + c0) : 0.f, b1 = bias ? __ldg(bias + c0 + 1) : 0.f;
+  const float b0 = bias ? __ldg(bias + c0) : 0.f, b1 = (bias && c0 + 1 < C) ? __ldg(bias + c0 + 1) : 0.f;
   bf16* yb = y + (((size_t)n * H + gy) * W) * ldy + c0;
 #pragma unroll
   for (int i = 0; i < XW; ++i) {
@@ -584,6 +584,11 @@ int launch_dwg_t(const bf16* x, int ldx, const bf16* dy, int lddy, float* dw, fl
 inline bool vec_ok(const void* a, int lda, const void* b, int ldb, int C) {
   return C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
 }
+// C < 8 on an 8-element pixel pitch (the 3-channel tensors of block c1): the tiled kernels stage whole 16-byte pixels and
+// guard weights / outputs per channel, so the pad lanes are only ever copied, never mixed into real channels
+inline bool small_ok(const void* a, int lda, const void* b, int ldb, int C) {
+  return C < 8 && lda % 8 == 0 && ldb % 8 == 0 && lda >= 8 && ldb >= 8 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
+}
 }  // namespace
 
 extern "C" {
@@ -591,7 +596,8 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
                      int H, int W, int C, int k, int flip, int accumulate, void* stream) {
   const long long total = (long long)N * H * W * C;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == DT_BF16 && vec_ok(x, ld_x, y, ld_y, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) {
+  if (dtype == DT_BF16 && ((vec_ok(x, ld_x, y, ld_y, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) ||
+                           small_ok(x, ld_x, y, ld_y, C))) {
     const bf16* xp = (const bf16*)x; bf16* yp = (bf16*)y;
 #define DWT(KK, PB) return launch_dw_t<KK, PB>(xp, ld_x, w, bias, yp, ld_y, N, H, W, C, flip, accumulate, s);
 #define DWT_K(PB) switch (k) { case 3: DWT(3, PB) case 5: DWT(5, PB) case 7: DWT(7, PB) case 9: DWT(9, PB) default: break; }
@@ -634,7 +640,8 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
 int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float* dw, float* db, int dtype, int N,
                        int H, int W, int C, int k, void* stream) {
   const long long npix = (long long)N * H * W;
-  if (dtype == DT_BF16 && vec_ok(x, ld_x, dy, ld_dy, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) {
+  if (dtype == DT_BF16 && ((vec_ok(x, ld_x, dy, ld_dy, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) ||
+                           small_ok(x, ld_x, dy, ld_dy, C))) {
     const bf16* xp = (const bf16*)x; const bf16* gp = (const bf16*)dy;
     cudaStream_t s = (cudaStream_t)stream;
 #define DWG(KK, PB) return launch_dwg_t<KK, PB>(xp, ld_x, gp, ld_dy, dw, db, N, H, W, C, s);

@@ -206,7 +206,7 @@ __global__ void k_colsum(const T* __restrict__ x, int ld, long long npix, int C,
 __global__ void __launch_bounds__(256) k_colsum_v8(const bf16* __restrict__ x, int ld, long long npix, int C,
                                                     float* __restrict__ out, long long chunk) {
   __shared__ float sacc[256];
-  const int groups = C / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;
+  const int groups = (C + 7) / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;  // ragged C: pitch == ceil8(C)
   const int tg = threadIdx.x % gl, tp = threadIdx.x / gl;
   const long long p0 = (long long)blockIdx.x * chunk, p1 = min(p0 + chunk, npix);
   const int cb = blockIdx.y * gl * 8, c0 = cb + tg * 8;
@@ -283,8 +283,8 @@ int dsgan_conv_wgrad(const dsgan_conv_desc* d, const void* in, const void* dout,
 }
 
 int dsgan_colsum(const void* x, int dtype, int ld, long long npix, int C, float* out, void* stream) {
-  if (dtype == DT_BF16 && C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16 == 0)) {
-    const int groups = C / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;
+  if (dtype == DT_BF16 && ld % 8 == 0 && (C % 8 == 0 || ld == (C + 7) / 8 * 8) && ((uintptr_t)x % 16 == 0)) {
+    const int groups = (C + 7) / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;
     const int cblocks = (C + gl * 8 - 1) / (gl * 8);
     // ~8 CTAs per SM over the whole launch, at least 16 rows per pixel lane so the 4-deep unroll is used
     long long blocks = (148 * 8 + cblocks - 1) / cblocks;

@@ -162,7 +162,7 @@ __device__ __forceinline__ uint4 ld8(const bf16* p) { return __ldg(reinterpret_c
 struct VLanes { int gl, pl, tg, tp; };
 __device__ __forceinline__ VLanes vlanes(int C) {
   VLanes l;
-  const int groups = C / 8;
+  const int groups = (C + 7) / 8;  // C % 8 != 0 only on a pitch of exactly ceil8(C): the pad lanes ride along
   l.gl = groups < 32 ? groups : 32;
   l.pl = blockDim.x / l.gl;
   l.tg = threadIdx.x % l.gl;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) k_in_stats_v8(const bf16* __restrict__ x,
       for (int e = 0; e < 8; ++e) { atomicAdd(&sacc[0][l.tg * 8 + e], s[e]); atomicAdd(&sacc[1][l.tg * 8 + e], ss[e]); }
       if (blockIdx.x == 0 && l.tp == 0) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) stats[((size_t)n * C + c0 + e) * 3] = k[e];
+        for (int e = 0; e < 8; ++e) if (c0 + e < C) stats[((size_t)n * C + c0 + e) * 3] = k[e];
       }
     }
     __syncthreads();
@@ -221,9 +221,9 @@ __device__ __forceinline__ uint32_t f2b(float2 v) {
 __device__ __forceinline__ void norm_consts(const float* stats, int n, int C, int c0, float inv, float2 (&rs)[4], float2 (&sh)[4]) {
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    float m0, r0, m1, r1;
-    mean_rstd(stats + ((size_t)n * C + c0 + 2 * e) * 3, inv, m0, r0);
-    mean_rstd(stats + ((size_t)n * C + c0 + 2 * e + 1) * 3, inv, m1, r1);
+    float m0 = 0.f, r0 = 0.f, m1 = 0.f, r1 = 0.f;
+    if (c0 + 2 * e < C) mean_rstd(stats + ((size_t)n * C + c0 + 2 * e) * 3, inv, m0, r0);
+    if (c0 + 2 * e + 1 < C) mean_rstd(stats + ((size_t)n * C + c0 + 2 * e + 1) * 3, inv, m1, r1);
     rs[e] = make_float2(r0, r1);
     sh[e] = make_float2(-m0 * r0, -m1 * r1);
   }
@@ -329,8 +329,9 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float* b0 = bst + ((size_t)n * C + c0 + 2 * e) * 2;
-      mg[e] = make_float2(b0[0] * inv, b0[2] * inv);
-      mgx[e] = make_float2(-b0[1] * inv, -b0[3] * inv);  // negated: t = g - mg + xh * (-mgx)
+      const bool v0 = c0 + 2 * e < C, v1 = c0 + 2 * e + 1 < C;
+      mg[e] = make_float2(v0 ? b0[0] * inv : 0.f, v1 ? b0[2] * inv : 0.f);
+      mgx[e] = make_float2(v0 ? -b0[1] * inv : 0.f, v1 ? -b0[3] * inv : 0.f);  // negated: t = g - mg + xh * (-mgx)
     }
 #pragma unroll 2
     for (long long p = p0 + l.tp; p < p1; p += l.pl) {
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
 // grid for the v8 kernels: (pixel chunks, N, channel blocks of <=256); the chunk shrinks on small planes so that the
 // launch still spreads over the 148 SMs
 inline dim3 v8grid(long long HW, int N, int C, int* chunk) {
-  const int groups = C / 8, gl = groups < 32 ? groups : 32;
+  const int groups = (C + 7) / 8, gl = groups < 32 ? groups : 32;
   const int cblocks = (C + gl * 8 - 1) / (gl * 8);
   int ch = 1024;
   while (ch > 64 && ((HW + ch - 1) / ch) * N * cblocks < 592) ch >>= 1;
@@ -380,9 +381,9 @@ inline dim3 v8grid(long long HW, int N, int C, int* chunk) {
   return dim3((unsigned)((HW + ch - 1) / ch), N, cblocks);
 }
 inline bool v8ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
-  if (C % 8) return false;
+  const int Cp = (C + 7) / 8 * 8;
   for (const void* p : ptrs) if (p && ((uintptr_t)p % 16)) return false;
-  for (int l : lds) if (l % 8) return false;
+  for (int l : lds) if (l % 8 || (C % 8 && l && l != Cp)) return false;  // ragged C: whole-pitch tensors only
   return true;
 }
 }  // namespace

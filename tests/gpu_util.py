@@ -15,6 +15,8 @@ def ctx_for(precision):
 def to_var(ctx, x_nchw):
     N, C, H, W = x_nchw.shape
     v = ctx.new(N, H, W, C)  # padded pixel pitch for odd channel counts in bf16 mode
+    if v.ld > C:
+        v.t[..., C:] = float("nan")  # poison the pad lanes: kernels may carry them along but must never mix them in
     v.t[..., :C] = x_nchw.permute(0, 2, 3, 1).to("cuda:0", ctx.tdtype)
     return v
 
@@ -35,6 +37,8 @@ def var_grad(v):
 def set_grad(ctx, v, dy_nchw):
     gp, ld, acc = v.grad_out()
     assert acc == 0 and ld == v.ld
+    if v.ld > v.C:
+        v.g[..., v.C:] = float("nan")
     v.g[..., :v.C] = dy_nchw.permute(0, 2, 3, 1).to("cuda:0", ctx.tdtype)
 
 
