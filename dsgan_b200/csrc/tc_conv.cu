@@ -14,6 +14,7 @@
 // 4-stage smem ring, double-buffered TMEM accumulator).
 #include "tc_common.cuh"
 #include "../../include/dsgan_b200.h"
+#include "sc_conv.cuh"
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -510,6 +511,10 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
   DS_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)w_slabs % 16 == 0), "tc_conv: unaligned");
   DS_REQUIRE(d->ci_pad % 64 == 0 && d->ci_pad >= d->Ci && d->co_pad >= d->Co, "tc_conv: bad slab padding");
   DS_REQUIRE(!d->dact || aux, "tc_conv: dact needs aux");
+  {
+    int rc = 0;   // 1/3/6/12-channel layers: CUDA-core direct convolution (sc_conv.cu), same contract
+    if (sc::conv_try(d, in, w_slabs, bias, out, pre_out, aux, stream, &rc)) return rc;
+  }
   const int BN = d->Co >= 256 ? 256 : (d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32));
   CUtensorMap ta, tb;
   if (map_input(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in, d->in_stride)) return 1;
@@ -540,6 +545,10 @@ int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void*
   DS_REQUIRE(dsgan_tc_conv_wgrad_supported(d->Cg, d->Cx, d->ld_g, d->ld_x), "tc_conv_wgrad: unsupported Cg=%d Cx=%d", d->Cg, d->Cx);
   DS_REQUIRE(d->ntaps >= 1 && d->ntaps <= MAX_TAPS && (d->x_stride == 1 || d->x_stride == 2), "tc_conv_wgrad: bad taps/stride");
   DS_REQUIRE(((uintptr_t)G % 16 == 0) && ((uintptr_t)X % 16 == 0), "tc_conv_wgrad: unaligned");
+  {
+    int rc = 0;
+    if (sc::wgrad_try(d, G, X, dW, stream, &rc)) return rc;
+  }
   const int BN = d->Cx >= 128 ? 128 : 64;
   CUtensorMap tg, tx;
   if (map_input(&tg, G, d->N, d->Hg, d->Wg, d->Cg, d->ld_g, 1)) return 1;

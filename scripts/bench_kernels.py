@@ -179,6 +179,29 @@ def main():
                  flops=2.0 * 16 * HW_ * HW_ * Ci * Co * 9)
             del x
 
+    # ---- small-channel layers (CUDA-core sc_conv backend): forward, and forward + backward (dgrad + wgrad + bias) ------
+    if want("smallch"):
+        for Ci, Co, k, st, pd, HW_, N_ in ((3, 64, 3, 1, 1, 256, 16), (64, 3, 3, 1, 1, 256, 16), (6, 32, 4, 2, 1, 256, 16),
+                                           (3, 12, 1, 1, 0, 256, 16), (12, 64, 1, 1, 0, 256, 16), (3, 64, 1, 1, 0, 256, 16)):
+            x = ctx.new(N_, HW_, HW_, Ci)
+            x.t.copy_(torch.randn(x.t.shape, device="cuda", generator=g))
+            P = params({"w": (Co, Ci, k, k) if k > 1 else (Co, Ci), "b": (Co,)})
+            Ho = (HW_ + 2 * pd - k) // st + 1
+            ctx.no_grad = True
+            ms = timeit(lambda: E.conv2d(ctx, x, P["w"], P["b"], k, st, pd))
+            ctx.no_grad = False
+            io = (N_ * HW_ * HW_ * x.ld + N_ * Ho * Ho * ((Co + 7) // 8 * 8)) * 2
+            emit(out, "sc_conv k%ds%d %d->%d @%dx%d N=%d fwd" % (k, st, Ci, Co, HW_, HW_, N_), ms, bytes_=io)
+
+            def fwd_bwd():
+                x.g = None
+                y = E.conv2d(ctx, x, P["w"], P["b"], k, st, pd)
+                y.grad_out()
+                ctx.backward()
+            ms2 = timeit(fwd_bwd)
+            emit(out, "sc_conv k%ds%d %d->%d fwd+dgrad+wgrad+colsum" % (k, st, Ci, Co), ms2, bytes_=3 * io)
+            del x
+
     # ---- config #5: generator-only inference, 32 x 512 x 512, bf16 ---------------------------------------------
     if want("infer"):
         from dsgan_b200.models import networks

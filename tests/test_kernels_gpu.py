@@ -26,6 +26,10 @@ def _g(seed):
     (2, 64, 16, 16, 64, 3, 1, 1, "relu"), (1, 128, 32, 32, 256, 3, 1, 1, None), (1, 64, 9, 13, 96, 3, 1, 1, "relu"),
     (2, 64, 32, 32, 128, 4, 2, 1, None), (1, 128, 32, 32, 256, 4, 1, 1, None), (1, 64, 18, 10, 32, 4, 2, 1, "leaky"),
     (1, 512, 8, 8, 512, 3, 1, 1, "relu"),
+    # small-channel layers (CUDA-core sc_conv backend in bf16 mode), incl. widths that are not a multiple of 4
+    (2, 12, 10, 14, 64, 1, 1, 0, None), (1, 64, 12, 10, 12, 1, 1, 0, "gelu"), (2, 12, 8, 8, 3, 1, 1, 0, None),
+    (1, 3, 10, 6, 32, 1, 1, 0, None), (1, 1, 9, 9, 16, 3, 1, 1, None), (2, 6, 30, 26, 32, 4, 2, 1, "leaky"),
+    (1, 64, 7, 9, 3, 3, 1, 1, None), (2, 3, 17, 19, 64, 3, 1, 1, "relu"), (1, 32, 12, 12, 6, 4, 2, 1, None),
 ])
 def test_conv2d(prec, cfg):
     N, Ci, H, W, Co, k, s, p, act = cfg
