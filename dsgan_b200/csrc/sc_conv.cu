@@ -387,6 +387,7 @@ bool conv_try(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, 
   const bool narrow_in = (d->Ci == 1 || d->Ci == 3 || d->Ci == 6 || d->Ci == 12) && d->Co <= 256;
   const bool narrow_out = !narrow_in && d->Co <= 16 && (d->Ci == 16 || d->Ci == 32 || d->Ci == 64 || d->Ci == 128);
   if (!narrow_in && !narrow_out) return false;
+  if (d->Ci == 1 && d->Co > 64) return false;   // (PatchGAN head's input-gradient 1 -> 256: measured faster on the tensor cores)
   const long long quads = (long long)d->N * d->nclass * d->Hg * ((d->Wg + PT - 1) / PT);
   const int V = narrow_out ? (d->Co <= 4 ? 4 : (d->Co <= 8 ? 8 : 16)) : 8;   // channels per output vector
   const int cog = narrow_out ? 1 : (d->Co + 7) / 8;
@@ -445,6 +446,7 @@ bool wgrad_try(const dsgan_tc_wgrad_desc* d, const void* G, const void* X, float
   auto narrow = [](int c) { return c == 1 || c == 3 || c == 6 || c == 12; };
   const bool ng = narrow(d->Cg), nx = narrow(d->Cx);
   if (!ng && !nx) return false;
+  if (d->ntaps == 1) return false;              // pointwise weight gradients: measured faster on the tensor cores
   // the wide side is the one with more channels; it is read in 8-channel groups
   const bool wide_is_g = nx && (!ng || d->Cg >= d->Cx);
   const int cw = wide_is_g ? d->Cg : d->Cx, cn = wide_is_g ? d->Cx : d->Cg;

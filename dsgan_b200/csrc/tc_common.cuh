@@ -104,6 +104,45 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  In the epilogues every lane owns one output ROW, so a warp's store
+// touches 32 different rows: with 16-byte stores each 32-byte sector is written in two halves by two instructions (ncu:
+// 134 M sector writes for 2.1 GB); one 32-byte store per lane writes whole sectors.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]),
+               "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// 32 fp32 values -> 64 bytes of bf16 at p (32-byte aligned): two 256-bit stores
+__device__ __forceinline__ void store_row32(void* p, const float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = bf16x2_bits(f[q * 16 + 2 * e], f[q * 16 + 2 * e + 1]);
+    st_global_v8(reinterpret_cast<uint8_t*>(p) + q * 32, w);
+  }
+}
+// 64 bytes of bf16 at p -> 32 fp32 values
+__device__ __forceinline__ void load_row32(const void* p, float (&a)[32]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t w[8];
+    ld_global_v8(reinterpret_cast<const uint8_t*>(p) + q * 32, w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a[q * 16 + 2 * e] = __uint_as_float(w[e] << 16);
+      a[q * 16 + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+    }
+  }
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -149,6 +149,9 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int oy = gy * p.os_ + p.oy0[cls], ox = gx * p.os_ + p.ox0[cls];
       const bool row_ok = gy < p.Hg && gx < p.Wg && oy < p.Ho && ox < p.Wo;
       const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
+      const bool wide = (p.ldc % 16 == 0) && ((uintptr_t)p.C % 32 == 0) &&
+                        (!p.pre || (p.ld_pre % 16 == 0 && (uintptr_t)p.pre % 32 == 0)) &&
+                        (!p.aux || (p.ld_aux % 16 == 0 && (uintptr_t)p.aux % 32 == 0));
       const bool vec_ok = (p.ldc % 8 == 0) && (!p.aux || p.ld_aux % 8 == 0) && (!p.pre || p.ld_pre % 8 == 0) &&
                           (((uintptr_t)p.C | (uintptr_t)p.aux | (uintptr_t)p.pre) % 16 == 0);
       mbar_wait(&tfull[acc], acc_phase);
@@ -173,47 +176,61 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           bf16* o = reinterpret_cast<bf16*>(p.C) + pix * p.ldc + col0;
           if (p.accumulate) {
-            const uint4* op = reinterpret_cast<const uint4*>(o);
+            float old[32];
+            if (wide) load_row32(o, old);
+            else {
+              const uint4* op = reinterpret_cast<const uint4*>(o);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = op[q];
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = op[q];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                f[q * 8 + e * 2] += __low2float(h);
-                f[q * 8 + e * 2 + 1] += __high2float(h);
+                for (int e = 0; e < 4; ++e) {
+                  old[q * 8 + e * 2] = __uint_as_float(w[e] << 16);
+                  old[q * 8 + e * 2 + 1] = __uint_as_float(w[e] & 0xffff0000u);
+                }
               }
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += old[j];
           }
           if (p.dact) {
             const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + pix * p.ld_aux + col0);
             float a[32];
+            if (wide) load_row32(ap, a);
+            else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = __ldg(ap + q);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(ap + q);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                a[q * 8 + e * 2] = h.x; a[q * 8 + e * 2 + 1] = h.y;
+                for (int e = 0; e < 4; ++e) {
+                  a[q * 8 + e * 2] = __uint_as_float(w[e] << 16);
+                  a[q * 8 + e * 2 + 1] = __uint_as_float(w[e] & 0xffff0000u);
+                }
               }
             }
             act_bwd_fast_mul<32>(p.dact, f, a);
           }
           if (p.pre) {
             uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.pre) + pix * p.ld_pre + col0);
+            if (wide) store_row32(pp, f);
+            else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              pp[q] = make_uint4(pack2(f[q * 8], f[q * 8 + 1]), pack2(f[q * 8 + 2], f[q * 8 + 3]),
-                                 pack2(f[q * 8 + 4], f[q * 8 + 5]), pack2(f[q * 8 + 6], f[q * 8 + 7]));
+              for (int q = 0; q < 4; ++q)
+                pp[q] = make_uint4(bf16x2_bits(f[q * 8], f[q * 8 + 1]), bf16x2_bits(f[q * 8 + 2], f[q * 8 + 3]),
+                                   bf16x2_bits(f[q * 8 + 4], f[q * 8 + 5]), bf16x2_bits(f[q * 8 + 6], f[q * 8 + 7]));
+            }
           }
           act_fwd_fast_vec<32>(p.act, f);
-          uint4* op = reinterpret_cast<uint4*>(o);
+          if (wide) store_row32(o, f);
+          else {
+            uint4* op = reinterpret_cast<uint4*>(o);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            op[q] = make_uint4(pack2(f[q * 8], f[q * 8 + 1]), pack2(f[q * 8 + 2], f[q * 8 + 3]),
-                               pack2(f[q * 8 + 4], f[q * 8 + 5]), pack2(f[q * 8 + 6], f[q * 8 + 7]));
+            for (int q = 0; q < 4; ++q)
+              op[q] = make_uint4(bf16x2_bits(f[q * 8], f[q * 8 + 1]), bf16x2_bits(f[q * 8 + 2], f[q * 8 + 3]),
+                                 bf16x2_bits(f[q * 8 + 4], f[q * 8 + 5]), bf16x2_bits(f[q * 8 + 6], f[q * 8 + 7]));
+          }
         }
         if (row_ok && col0 < p.Co && !(col0 + 32 <= p.Co && vec_ok)) {
           // narrow / unaligned output (Co = 1, 3, 6, 12 ...): guarded scalar epilogue

@@ -198,6 +198,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      // 256-bit row accesses when every row segment is 32-byte aligned
+      const bool wide = MODE != 2 && (p.ldc % 16 == 0) && ((uintptr_t)p.C % 32 == 0) &&
+                        (!p.pre || (p.ld_pre % 16 == 0 && (uintptr_t)p.pre % 32 == 0)) &&
+                        (!p.aux || (p.ld_aux % 16 == 0 && (uintptr_t)p.aux % 32 == 0));
 #pragma unroll 1
       for (int c = part; c < BN / 32; c += nparts) {
         uint32_t v[32];
@@ -224,47 +228,61 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           bf16* o = reinterpret_cast<bf16*>(p.C) + (size_t)row * p.ldc + col0;
           if (p.accumulate) {
-            const uint4* op = reinterpret_cast<const uint4*>(o);
+            float old[32];
+            if (wide) load_row32(o, old);
+            else {
+              const uint4* op = reinterpret_cast<const uint4*>(o);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = op[q];
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = op[q];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[e]);
-                f[q * 8 + e * 2] += __low2float(h);
-                f[q * 8 + e * 2 + 1] += __high2float(h);
+                for (int e = 0; e < 4; ++e) {
+                  old[q * 8 + e * 2] = __uint_as_float(w[e] << 16);
+                  old[q * 8 + e * 2 + 1] = __uint_as_float(w[e] & 0xffff0000u);
+                }
               }
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += old[j];
           }
           if (p.dact) {
             const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.aux) + (size_t)row * p.ld_aux + col0);
             float a[32];
+            if (wide) load_row32(ap, a);
+            else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = __ldg(ap + q);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = __ldg(ap + q);
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-                a[q * 8 + e * 2] = h.x; a[q * 8 + e * 2 + 1] = h.y;
+                for (int e = 0; e < 4; ++e) {
+                  a[q * 8 + e * 2] = __uint_as_float(w[e] << 16);
+                  a[q * 8 + e * 2 + 1] = __uint_as_float(w[e] & 0xffff0000u);
+                }
               }
             }
             act_bwd_fast_mul<32>(p.dact, f, a);
           }
           if (p.pre) {
             uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.pre) + (size_t)row * p.ld_pre + col0);
+            if (wide) store_row32(pp, f);
+            else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              pp[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                                 pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+              for (int q = 0; q < 4; ++q)
+                pp[q] = make_uint4(bf16x2_bits(f[q * 8], f[q * 8 + 1]), bf16x2_bits(f[q * 8 + 2], f[q * 8 + 3]),
+                                   bf16x2_bits(f[q * 8 + 4], f[q * 8 + 5]), bf16x2_bits(f[q * 8 + 6], f[q * 8 + 7]));
+            }
           }
           act_fwd_fast_vec<32>(p.act, f);
-          uint4* op = reinterpret_cast<uint4*>(o);
+          if (wide) store_row32(o, f);
+          else {
+            uint4* op = reinterpret_cast<uint4*>(o);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            op[q] = make_uint4(pack_bf16x2(f[q * 8], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                               pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+            for (int q = 0; q < 4; ++q)
+              op[q] = make_uint4(bf16x2_bits(f[q * 8], f[q * 8 + 1]), bf16x2_bits(f[q * 8 + 2], f[q * 8 + 3]),
+                                 bf16x2_bits(f[q * 8 + 4], f[q * 8 + 5]), bf16x2_bits(f[q * 8 + 6], f[q * 8 + 7]));
+          }
         }
         }
         __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge before the next chunk

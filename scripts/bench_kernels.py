@@ -38,7 +38,7 @@ def timeit(fn, iters=10, warm=3, flush=True):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    tot = 0.0
+    ts = []
     for _ in range(iters):
         if flush:
             flush_l2()
@@ -47,8 +47,9 @@ def timeit(fn, iters=10, warm=3, flush=True):
         fn()
         e1.record()
         torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / iters
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]   # median: robust against a one-off stall (allocator growth, lazy module load)
 
 
 def graphed(fn):
