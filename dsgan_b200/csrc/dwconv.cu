@@ -465,14 +465,30 @@ __global__ void __launch_bounds__(256) k_dwconv_t(const bf16* __restrict__ x, in
   const int c0 = c_base + pair * 2;
   const float b0 = bias ? __ldg(bias + c0) : 0.f, b1 = (bias && c0 + 1 < C) ? __ldg(bias + c0 + 1) : 0.f;
   bf16* yb = y + (((size_t)n * H + gy) * W) * ldy + c0;
+  if (acc_out) {
+    // accumulate (gradient fan-in): fetch the old values in batches of 8 independent loads before touching them
+#pragma unroll
+    for (int i0 = 0; i0 < XW; i0 += 8) {
+      uint32_t oldw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int gx = x0 + xs + i0 + j;
+        oldw[j] = (i0 + j < XW && gx < W) ? *reinterpret_cast<const uint32_t*>(yb + (size_t)gx * ldy) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (i0 + j < XW) {
+          const float2 old = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&oldw[j]));
+          acc[i0 + j].x += old.x; acc[i0 + j].y += old.y;
+        }
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < XW; ++i) {
     const int gx = x0 + xs + i;
     if (gx >= W) break;
-    float2 o = make_float2(acc[i].x + b0, acc[i].y + b1);
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(yb + (size_t)gx * ldy);
-    if (acc_out) { const float2 old = __bfloat1622float2(*dst); o.x += old.x; o.y += old.y; }
-    *dst = __floats2bfloat162_rn(o.x, o.y);
+    *reinterpret_cast<__nv_bfloat162*>(yb + (size_t)gx * ldy) = __floats2bfloat162_rn(acc[i].x + b0, acc[i].y + b1);
   }
 }
 

@@ -112,11 +112,13 @@ class ParamTree(nn.Module):
 
 def _block(ctx: Ctx, P, p, x: Var, out: Var = None, need_dx=True):
     """ConvNeXt Block (MixConvNeXtML.py:230-243): dw7x7 -> IN -> Linear(C,4C) -> GELU -> Linear(4C,P) (+) 1x1 shortcut."""
+    # the shortcut writes y first and pwconv2 accumulates into it, so that in the backward pass (reverse order) the depthwise
+    # input-gradient OVERWRITES dL/dx and the shortcut's GEMM epilogue does the fan-in add (cheaper than a depthwise RMW)
+    y = conv2d(ctx, x, P[p + ".shortcut.weight"], None, 1, out=out, need_dx=need_dx)
     t = dwconv(ctx, x, P[p + ".dwconv.weight"], P[p + ".dwconv.bias"], 7, need_dx=need_dx)
     t = inorm(ctx, t)
     h = conv2d(ctx, t, P[p + ".pwconv1.weight"], P[p + ".pwconv1.bias"], 1, act=ACT_GELU)
-    y = conv2d(ctx, h, P[p + ".pwconv2.weight"], P[p + ".pwconv2.bias"], 1, out=out)
-    conv2d(ctx, x, P[p + ".shortcut.weight"], None, 1, out=y, acc=1, need_dx=need_dx)
+    conv2d(ctx, h, P[p + ".pwconv2.weight"], P[p + ".pwconv2.bias"], 1, out=y, acc=1)
     return y
 
 

@@ -141,6 +141,8 @@ def main():
         b = torch.zeros(128, device="cuda")
         dw, db = torch.zeros_like(w), torch.zeros_like(b)
         emit(out, "dwconv7 fwd 16x256x256x128 bf16", timeit(lambda: L.dwconv_fwd(x.ptr, 128, w.data_ptr(), b.data_ptr(), y.ptr, 128, 1, 16, 256, 256, 128, 7, 0, 0, s)), bytes_=2 * nb)
+        emit(out, "dwconv7 dgrad (flip, overwrite)", timeit(lambda: L.dwconv_fwd(dy.ptr, 128, w.data_ptr(), None, dx.ptr, 128, 1, 16, 256, 256, 128, 7, 1, 0, s)), bytes_=2 * nb)
+        emit(out, "dwconv7 dgrad (flip, accumulate)", timeit(lambda: L.dwconv_fwd(dy.ptr, 128, w.data_ptr(), None, dx.ptr, 128, 1, 16, 256, 256, 128, 7, 1, 1, s)), bytes_=3 * nb)
         emit(out, "dwconv7 wgrad", timeit(lambda: L.dwconv_wgrad(x.ptr, 128, dy.ptr, 128, dw.data_ptr(), db.data_ptr(), 1, 16, 256, 256, 128, 7, s)), bytes_=2 * nb)
         del x, y, dy, dx
 
