@@ -370,14 +370,31 @@ __global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict_
   }
 }
 
-// grid for the v8 kernels: (pixel chunks, N, channel blocks of <=256); the chunk shrinks on small planes so that the
-// launch still spreads over the 148 SMs
-inline dim3 v8grid(long long HW, int N, int C, int* chunk) {
+// grid for the v8 kernels: (pixel chunks, N, channel blocks of <=256).  All blocks do the same work, so the chunk is chosen
+// to make the grid a whole number of waves of the kernel's resident blocks (148 SMs x occupancy): a 1.7-wave grid idles a
+// quarter of the machine in its second wave.  Small planes fall back to >= 64-pixel chunks.
+template <typename K>
+inline int resident_blocks(K kern, int* cache) {
+  if (*cache == 0) {
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0);
+    *cache = sms * (occ > 0 ? occ : 1);
+  }
+  return *cache;
+}
+inline dim3 v8grid(long long HW, int N, int C, int* chunk, int slots) {
   const int groups = (C + 7) / 8, gl = groups < 32 ? groups : 32;
   const int cblocks = (C + gl * 8 - 1) / (gl * 8);
-  int ch = 1024;
-  while (ch > 64 && ((HW + ch - 1) / ch) * N * cblocks < 592) ch >>= 1;
-  *chunk = ch;
+  const long long base = (long long)N * cblocks;
+  long long bpi = slots / base;            // blocks per (image, channel block) for one full wave
+  if (bpi < 1) bpi = 1;
+  long long ch = (HW + bpi - 1) / bpi;
+  while (ch > 2048) { bpi *= 2; ch = (HW + bpi - 1) / bpi; }   // long chunks: more waves instead
+  if (ch < 64) ch = 64;
+  if (ch > HW) ch = HW;
+  *chunk = (int)ch;
   return dim3((unsigned)((HW + ch - 1) / ch), N, cblocks);
 }
 inline bool v8ok(int C, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
@@ -394,7 +411,8 @@ int dsgan_inorm_stats(const void* x, int ld_x, int dtype, int N, long long HW, i
   cudaMemsetAsync(stats, 0, sizeof(float) * 3 * N * C, s);
   if (dtype == DT_BF16 && v8ok(C, {x}, {ld_x})) {
     int ch;
-    dim3 g8 = v8grid(HW, N, C, &ch);
+    static int slots = 0;
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_stats_v8, &slots));
     k_in_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, HW, C, stats, ch);
     return DS_LAUNCHED("inorm_stats_v8");
   }
@@ -406,7 +424,8 @@ int dsgan_inorm_apply(const void* x, int ld_x, const float* stats, const void* r
                       int dtype, int N, long long HW, int C, int act, void* stream) {
   if (dtype == DT_BF16 && v8ok(C, {x, res, y}, {ld_x, res ? ld_res : 0, ld_y})) {
     int ch;
-    dim3 g8 = v8grid(HW, N, C, &ch);
+    static int slots = 0;
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_apply_v8, &slots));
     k_in_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (bf16*)y,
                                                         ld_y, HW, C, act, ch);
     return DS_LAUNCHED("inorm_apply_v8");
@@ -422,7 +441,8 @@ int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const voi
   cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * N * C, s);
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy}, {ld_x, res ? ld_res : 0, ld_dy})) {
     int ch;
-    dim3 g8 = v8grid(HW, N, C, &ch);
+    static int slots = 0;
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_stats_v8, &slots));
     k_in_bwd_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (const bf16*)dy, ld_dy, HW,
                                           C, act, bstats, ch);
     return DS_LAUNCHED("inorm_bwd_stats_v8");
@@ -437,7 +457,8 @@ int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const voi
                           int acc_dres, int dtype, int N, long long HW, int C, int act, void* stream) {
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy, dx, dres}, {ld_x, res ? ld_res : 0, ld_dy, ld_dx, dres ? ld_dres : 0})) {
     int ch;
-    dim3 g8 = v8grid(HW, N, C, &ch);
+    static int slots = 0;
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8, &slots));
     k_in_bwd_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
                                                             (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
                                                             (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch);
