@@ -135,7 +135,8 @@ def run_ours(args):
     from dsgan_b200.options.train_options import TrainOptions
 
     opt = TrainOptions().parse("/tmp/none", "/tmp/dsgan_b200_bench",
-                               argv=["--precision", args.precision, "--gpu_ids", str(local), "--batchSize", str(args.batch)],
+                               argv=["--precision", args.precision, "--gpu_ids", str(local), "--batchSize", str(args.batch),
+                                     "--cuda_graph", "0" if args.no_graph else "1"],
                                quiet=True)
     torch.manual_seed(20)
     import contextlib
@@ -171,7 +172,7 @@ def run_ours(args):
 
     # ---- device-resident arm ("value") ---------------------------------------------------------
     model.set_input(batch)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 0 if args.no_graph else 3)):   # (graph mode: two eager steps + the capture step are never timed)
         model.optimize_parameters()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -179,6 +180,10 @@ def run_ours(args):
     n0 = L.cdll.dsgan_launch_count()
     ms = timed(model.optimize_parameters, args.steps)
     launches = L.cdll.dsgan_launch_count() - n0
+    gs = getattr(model, "_gs", None)
+    graphed = gs is not None and gs.get("plan") is not None
+    if graphed:   # replayed steps launch the kernels recorded at capture; the library's counter only sees eager launches
+        launches += args.steps * gs["kernels_per_replay"]
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end arm: host batch in, losses out, every step -------------------------------------
@@ -219,7 +224,9 @@ def run_ours(args):
         "config": {"workload": "DS-GAN training step (MixConvNeXtML G + PatchGAN D + VGG/L1/TV/SSIM losses, 2x Adam), "
                                "per-GPU batch %d, 256x256, random-init weights" % b,
                    "per_gpu_batch": b, "global_batch": imgs, "parallelism": "dp%d" % world,
-                   "l2_note": "per-step working set (activations, >5 GB) far exceeds the 126 MB L2"},
+                   "l2_note": "per-step working set (activations, >5 GB) far exceeds the 126 MB L2",
+                   "launch": "CUDA-graph replay of the step (image pool / NCCL eager between segments)" if graphed
+                             else "eager launches"},
         "e2e": {"value": imgs * args.steps / (ms_e2e * 1e-3), "unit": "img/s",
                 "h2d_bytes_per_step": int(hostA.numel() * 4 + hostB.numel() * 4), "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches),
@@ -248,6 +255,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="print the per-kernel profile to stderr")
+    ap.add_argument("--no-graph", dest="no_graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

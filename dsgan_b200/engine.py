@@ -307,17 +307,18 @@ class Ctx:
         hit = w.cache.get(key)
         cur = torch.cuda.current_stream(self.device)
         sid = cur.cuda_stream
+        cap = torch.cuda.is_current_stream_capturing()
+        # Cross-stream ordering is only needed INSIDE one step (a forked branch sharing weights with the main stream): fork /
+        # join already order consecutive steps.  An event recorded outside a graph capture is never waited on from inside one.
         if hit is None or hit[0] != w.epoch:
             buf = hit[1] if hit is not None else torch.empty(k * k * Op * Ip, dtype=torch.bfloat16, device=self.device)
-            if hit is not None and hit[3] != sid:
-                cur.wait_event(hit[2])  # a re-pack must not overtake readers of the previous contents on another stream
             self.L.pack_conv_weight(w.ptr, buf.data_ptr(), O, I, Op, Ip, k, k, wst[0], wst[1], wst[2], wst[3], 0,
                                     self.stream)
             ev = torch.cuda.Event()
             ev.record(cur)
-            w.cache[key] = hit = (w.epoch, buf, ev, sid)
-        elif hit[3] != sid:
-            cur.wait_event(hit[2])      # packed on another stream (forked branch sharing the same weights)
+            w.cache[key] = hit = (w.epoch, buf, ev, sid, cap)
+        elif hit[3] != sid and hit[4] == cap:
+            cur.wait_event(hit[2])      # packed on another stream in this step (forked branch sharing the same weights)
         return hit[1].data_ptr(), Op, Ip
 
     def _tc_conv(self, geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):

@@ -43,6 +43,8 @@ class Pix2PixModel(BaseModel):
                                       not opt.no_dropout, opt.init_type, self.gpu_ids)
         self.ctx = networks.get_ctx(self.device, self.precision)
         self.world = parallel.world_size()
+        self._in_buf, self._gs = {}, None
+        self.use_graph = bool(int(getattr(opt, "cuda_graph", 1))) and self.isTrain
         if self.isTrain:
             use_sigmoid = opt.no_lsgan
             d_in = opt.input_nc + opt.output_nc if self.use_condition == 1 else opt.input_nc
@@ -64,10 +66,23 @@ class Pix2PixModel(BaseModel):
                     parallel.broadcast_params(net.flat_buffers()[0], 0)
 
     # ---- reference API ---------------------------------------------------------------------
+    def _to_input_buffer(self, name, src):
+        """Training inputs land in persistent device buffers (same address every step: a captured graph can read them, and
+        the steady state allocates nothing); a shape change re-allocates."""
+        buf = self._in_buf.get(name)
+        if buf is None or buf.shape != src.shape:
+            buf = self._in_buf[name] = torch.empty(src.shape, dtype=torch.float32, device=self.device)
+        buf.copy_(src, non_blocking=True)
+        return buf
+
     def set_input(self, input):
         AtoB = self.opt.which_direction == "AtoB"
-        self.real_A = input["A" if AtoB else "B"].to(self.device, non_blocking=True).float().contiguous()
-        self.real_B = input["B" if AtoB else "A"].to(self.device, non_blocking=True).float().contiguous()
+        a, b = input["A" if AtoB else "B"], input["B" if AtoB else "A"]
+        if self.isTrain:
+            self.real_A, self.real_B = self._to_input_buffer("A", a), self._to_input_buffer("B", b)
+        else:
+            self.real_A = a.to(self.device, non_blocking=True).float().contiguous()
+            self.real_B = b.to(self.device, non_blocking=True).float().contiguous()
         self.image_paths = input["A_paths" if AtoB else "B_paths"]
 
     def forward(self):
@@ -94,8 +109,7 @@ class Pix2PixModel(BaseModel):
         ctx = self.ctx
         ctx.param_grads = True
         if self.use_condition == 1:
-            fake_AB = self.fake_AB_pool.query(torch.cat((self.real_A, self.fake_B), 1))
-            xf = image_to_nhwc(ctx, fake_AB.contiguous())
+            xf = image_to_nhwc(ctx, self._pooled_fake().contiguous())
             xr = self._pair(self.real_A, self.real_B)
         else:
             xf, xr = image_to_nhwc(ctx, self.fake_B), image_to_nhwc(ctx, self.real_B)
@@ -146,20 +160,126 @@ class Pix2PixModel(BaseModel):
     def _allreduce(self, net):
         parallel.allreduce_grads(net.flat_buffers()[1])
 
-    def optimize_parameters(self):
-        self._loss.copy_(self._loss_init)
-        self.forward()
-        if self.use_gan == 1:
+    def _pooled_fake(self):
+        """ImagePool.query(cat(real_A, fake_B)) (pix2pix_model.py:145).  Host logic with python `random`: while a graph is
+        being captured / replayed it runs eagerly BETWEEN the graph segments and hands its result over in a static buffer."""
+        if self._gs is not None and self._gs.get("pool_in") is not None:
+            return self._gs["pool_in"]
+        return self.fake_AB_pool.query(torch.cat((self.real_A, self.fake_B), 1))
+
+    # The step as a list of segments; "eager" ones (image pool, NCCL all-reduce) are never captured.
+    def _segments(self):
+        gscale = parallel.adam_grad_scale(self.world)
+        graphed = self._gs is not None
+        adam = (lambda o: o.record_step(gscale)) if graphed else (lambda o: o.step(gscale))
+
+        def seg_forward():
+            self._loss.copy_(self._loss_init)
+            self.forward()
+
+        def seg_pool():   # eager: feed the image pool's answer to the captured D step
+            gs = self._gs
+            if self.use_gan == 1 and self.use_condition == 1:
+                out = self.fake_AB_pool.query(torch.cat((self.real_A, self.fake_B), 1))
+                gs["pool_in"].copy_(out)
+
+        def seg_d():
             self.set_requires_grad(self.netD, True)
             self.optimizer_D.zero_grad()
             self.backward_D()
-            self._allreduce(self.netD)
-            self.optimizer_D.step(parallel.adam_grad_scale(self.world))
-        self.set_requires_grad(self.netD, False)
-        self.optimizer_G.zero_grad()
-        self.backward_G()
-        self._allreduce(self.netG)
-        self.optimizer_G.step(parallel.adam_grad_scale(self.world))
+
+        def seg_d_adam_and_g():
+            if self.use_gan == 1:
+                adam(self.optimizer_D)
+            self.set_requires_grad(self.netD, False)
+            self.optimizer_G.zero_grad()
+            self.backward_G()
+
+        def seg_g_adam():
+            adam(self.optimizer_G)
+
+        segs = [("graph", seg_forward)]
+        if graphed:
+            segs.append(("eager", seg_pool))
+        if self.use_gan == 1:
+            segs.append(("graph", seg_d))
+            if self.world > 1:
+                segs.append(("eager", lambda: self._allreduce(self.netD)))
+        segs.append(("graph", seg_d_adam_and_g))
+        if self.world > 1:
+            segs.append(("eager", lambda: self._allreduce(self.netG)))
+        segs.append(("graph", seg_g_adam))
+        return segs
+
+    def _eager_step(self):
+        gs, self._gs = self._gs, None      # plain path: pool queried inline, Adam with host-side scalars
+        try:
+            for _kind, fn in self._segments():
+                fn()
+        finally:
+            self._gs = gs
+
+    def _flat_ptrs(self):
+        return tuple(t.data_ptr() for net in (self.netG, self.netD, self.vgg) for t in net.flat_buffers()[:2])
+
+    def _capture(self, gs):
+        """Capture the graph segments of one step (nothing executes).  All segments share one memory pool: G's forward
+        activations (segment 1) are consumed and freed by the backward pass captured in a later segment."""
+        torch.cuda.synchronize()
+        if self.use_gan == 1 and self.use_condition == 1:
+            n, ca, h, w = self.real_A.shape
+            gs["pool_in"] = torch.empty((n, ca + self.real_B.shape[1], h, w), dtype=torch.float32, device=self.device)
+        else:
+            gs["pool_in"] = None
+        for o in (self.optimizer_G, self.optimizer_D):
+            o._state()
+        self._gs = gs
+        pool = torch.cuda.graph_pool_handle()
+        n0 = self.ctx.L.cdll.dsgan_launch_count()
+        plan, run = [], []
+        for kind, fn in self._segments():
+            if kind == "graph" and run and run[-1][0] == "graph":
+                run[-1][1].append(fn)          # merge adjacent graph segments
+            else:
+                run.append((kind, [fn]))
+        for kind, fns in run:
+            if kind == "eager":
+                plan.append(("eager", fns))
+                continue
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                for fn in fns:
+                    fn()
+            plan.append(("graph", g))
+        gs["plan"], gs["ptrs"] = plan, self._flat_ptrs()
+        gs["kernels_per_replay"] = int(self.ctx.L.cdll.dsgan_launch_count() - n0)   # launches recorded into the graphs
+        torch.cuda.synchronize()
+
+    def _replay(self, gs):
+        if self.use_gan == 1:
+            self.optimizer_D.advance()
+        self.optimizer_G.advance()
+        for kind, item in gs["plan"]:
+            if kind == "graph":
+                item.replay()
+            else:
+                for fn in item:
+                    fn()
+
+    def optimize_parameters(self):
+        if not (self.use_graph and self.ctx.profile is None):
+            return self._eager_step()
+        key = (tuple(self.real_A.shape), tuple(self.real_B.shape), self.real_A.data_ptr(), self.real_B.data_ptr(),
+               self.world, self.ctx.use_streams)
+        gs = self._gs
+        if gs is None or gs["key"] != key or (gs.get("plan") is not None and gs["ptrs"] != self._flat_ptrs()):
+            self._gs = gs = {"key": key, "warm": 0, "plan": None, "pool_in": None}
+        if gs["plan"] is None:
+            if gs["warm"] < 2:      # two eager steps first: lazy one-time work (function attributes, frozen-weight packing,
+                gs["warm"] += 1     # allocator growth) must not land inside a capture
+                return self._eager_step()
+            self._capture(gs)
+        self._replay(gs)
 
     # ---- loss attributes (0-d device tensors; float() synchronises, like the reference's) -----
     def __getattr__(self, name):

@@ -27,5 +27,31 @@ class FlatAdam:
                         float(g["lr"]), g["betas"][0], g["betas"][1], g["eps"], self.t, float(grad_scale), None,
                         ctx.stream)
 
+    # ---- CUDA-graph form: the kernel reads lr/(1-b1^t) and sqrt(1-b2^t) from device memory ---------------------
+    def _state(self):
+        flat, grad, _ = self.net.flat_buffers()
+        if self.m is None or self.m.device != flat.device:
+            self.m = torch.zeros_like(flat)
+            self.v = torch.zeros_like(flat)
+        if getattr(self, "hyper", None) is None or self.hyper.device != flat.device:
+            self.hyper = torch.zeros(2, dtype=torch.float32, device=flat.device)
+        return flat, grad
+
+    def record_step(self, grad_scale=1.0):
+        """Launch (or capture) the update kernel without advancing t; pair every replay with advance()."""
+        flat, grad = self._state()
+        ctx = self.net.ctx()
+        g = self.param_groups[0]
+        ctx.L.adam_step_dev(flat.data_ptr(), grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), flat.numel(),
+                            self.hyper.data_ptr(), g["betas"][0], g["betas"][1], g["eps"], float(grad_scale), None, ctx.stream)
+
+    def advance(self):
+        """t += 1 and refresh the device-side scalars (stream-ordered before the graph that contains record_step)."""
+        self._state()
+        ctx = self.net.ctx()
+        self.t += 1
+        g = self.param_groups[0]
+        ctx.L.adam_hyper(self.hyper.data_ptr(), float(g["lr"]), g["betas"][0], g["betas"][1], self.t, ctx.stream)
+
     def state_dict(self):
         return {"t": self.t, "m": self.m, "v": self.v, "param_groups": self.param_groups}

@@ -42,6 +42,8 @@ BASE_FLAGS = [
     ("--w_tv", dict(default=1)), ("--w_ss", dict(default=1.25)), ("--use_condition", dict(default=1)),
     # extension (not in the reference): activation precision of the sm_100a kernels
     ("--precision", dict(type=str, default="bf16", choices=["bf16", "fp32"])),
+    # extension: replay optimize_parameters() as CUDA graphs after two eager warm-up steps (0 = always eager)
+    ("--cuda_graph", dict(type=int, default=1)),
 ]
 
 

@@ -230,6 +230,12 @@ int dsgan_ssim_combine(const float* sums, float inv_size, int NC, float out_scal
  * p_bf16 (may be NULL) receives the bf16 copy of the updated parameters. */
 int dsgan_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                     float eps, int step_t, float grad_scale, void* p_bf16, void* stream);
+/* Graph-replayable form: the step-dependent scalars live in device memory.  dsgan_adam_hyper writes
+ * hyper[0] = lr / (1 - beta1^t), hyper[1] = sqrt(1 - beta2^t) (a by-value kernel argument, so the host may run ahead);
+ * dsgan_adam_step_dev is dsgan_adam_step reading them (lr*m_hat/(sqrt(v_hat)+eps) in the same operation order). */
+int dsgan_adam_hyper(float* hyper, float lr, float beta1, float beta2, int step_t, void* stream);
+int dsgan_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, const float* hyper, float beta1,
+                        float beta2, float eps, float grad_scale, void* p_bf16, void* stream);
 /* dst bf16 [cols,rows] = transpose(src fp32 [rows,cols]) — packed operand for input-gradient GEMMs. */
 int dsgan_pack_transpose_bf16(const float* src, void* dst, int rows, int cols, void* stream);
 
