@@ -10,6 +10,8 @@ scaling (16 images per GPU, global batch 128 at 8 GPUs = configs[2]).  Prints ON
 on the GPU box) on a bounded sample of the same workload.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -245,6 +247,28 @@ def run_ours(args):
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under torchrun), so the
+    # process-level stdout is pointed at stderr for the whole run and the result line is written to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    lines = [l for l in out.getvalue().splitlines() if l.startswith("{")]
+    for l in out.getvalue().splitlines():
+        if not l.startswith("{"):
+            print(l, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
