@@ -112,12 +112,23 @@ __device__ __forceinline__ void gelu_parts_fast(float x, float& cdf, float& pdf)
   gelu_parts_fast2(make_float2(x, x), c, p);
   cdf = c.x; pdf = p.x;
 }
+// gelu'(x) = Phi(x) + x phi(x) directly: gelu'(x) - 0.5 is odd, = x * Q(t), t = 2 x^2 / 25 - 1, |x| clamped to 5 (beyond: 1 + 1e-5
+// and -1e-5 instead of 1 and 0), Q of degree 12; fp32 Horner error 9.8e-6 against float64.  No MUFU, ~19 issue slots per pair.
+__device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
+  float2 xc = make_float2(fminf(fmaxf(x.x, -5.0f), 5.0f), fminf(fmaxf(x.y, -5.0f), 5.0f));
+  const float2 t = __ffma2_rn(__fmul2_rn(xc, xc), f2dup(0.08f), f2dup(-1.0f));
+  const float q[13] = {1.421335801e-01f, -7.509966350e-02f, 6.658681821e-02f, -7.208436384e-02f, 8.015732403e-02f, -8.186698327e-02f, 8.084683210e-02f, -7.745690087e-02f, 5.105054164e-02f, -1.767319918e-02f, 1.795447979e-02f, -2.475356668e-02f, 1.020706059e-02f};
+  float2 p = __ffma2_rn(f2dup(q[12]), t, f2dup(q[11]));
+#pragma unroll
+  for (int i = 10; i >= 0; --i) p = __ffma2_rn(p, t, f2dup(q[i]));
+  return __ffma2_rn(p, xc, f2dup(0.5f));
+}
 __device__ __forceinline__ float act_fwd_fast(int act, float v) {
   if (act == ACT_GELU) return v * gelu_cdf_fast2(make_float2(v, v)).x;
   return act_fwd(act, v);
 }
 __device__ __forceinline__ float act_bwd_fast(int act, float a) {
-  if (act == ACT_GELU) { float c, p; gelu_parts_fast(a, c, p); return fmaf(a, p, c); }
+  if (act == ACT_GELU) return gelu_grad_fast2(make_float2(a, a)).x;
   return act_bwd(act, a);
 }
 __device__ __forceinline__ float2 act_fwd_fast2(int act, float2 u) {
@@ -126,7 +137,7 @@ __device__ __forceinline__ float2 act_fwd_fast2(int act, float2 u) {
   return make_float2(act_fwd(act, u.x), act_fwd(act, u.y));
 }
 __device__ __forceinline__ float2 act_bwd_fast2(int act, float2 u) {
-  if (act == ACT_GELU) { float2 c, p; gelu_parts_fast2(u, c, p); return __ffma2_rn(u, p, c); }
+  if (act == ACT_GELU) return gelu_grad_fast2(u);
   if (act == ACT_NONE) return make_float2(1.f, 1.f);
   return make_float2(act_bwd(act, u.x), act_bwd(act, u.y));
 }
@@ -150,10 +161,7 @@ __device__ __forceinline__ void act_bwd_fast_mul(int act, float (&v)[N], const f
   if (act == ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < N; j += 2) {
-      float2 c, p;
-      const float2 x = make_float2(a[j], a[j + 1]);
-      gelu_parts_fast2(x, c, p);
-      const float2 d = __ffma2_rn(x, p, c);
+      const float2 d = gelu_grad_fast2(make_float2(a[j], a[j + 1]));
       v[j] *= d.x; v[j + 1] *= d.y;
     }
   } else if (act != ACT_NONE) {
