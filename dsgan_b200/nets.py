@@ -125,6 +125,11 @@ def _block(ctx: Ctx, P, p, x: Var, out: Var = None, need_dx=True):
 def _upsample(ctx: Ctx, P, p, x: Var, skip: Var):
     """upSample (MixConvNeXtML.py:60-66): ConvT -> IN -> GELU written straight into the concat buffer."""
     t = conv_transpose2d(ctx, x, P[p + ".weight"], P[p + ".bias"])
+    par = skip.parent
+    if par is not None and par.parent is None and skip.coff == t.C and par.C == t.C + skip.C:
+        cat = par        # the skip tensor was produced in place in channels [C, 2C) of this concat buffer: nothing to copy
+        inorm(ctx, t, act=ACT_GELU, out=cat.slice(0, t.C))
+        return cat
     cat = ctx.new(t.N, t.H, t.W, t.C + skip.C)
     inorm(ctx, t, act=ACT_GELU, out=cat.slice(0, t.C))
     concat_into(ctx, cat, t.C, skip)
@@ -176,8 +181,11 @@ def generator_forward(ctx: Ctx, P, x: Var) -> Var:
     with fk:
         loc = _local(ctx, P, x)
     R, t = [], x
-    for i, (name, _cin, _cout) in enumerate(specs.ENC):
-        t = _block(ctx, P, name, t if i == 0 else maxpool(ctx, t, 2), need_dx=i > 0)
+    for i, (name, _cin, cout) in enumerate(specs.ENC):
+        out = None
+        if i < 4:   # R1..R4 are the decoder's skip tensors: write them straight into channels [C, 2C) of its concat buffer
+            out = ctx.new(x.N, x.H >> i, x.W >> i, 2 * cout).slice(cout, cout)
+        t = _block(ctx, P, name, t if i == 0 else maxpool(ctx, t, 2), out=out, need_dx=i > 0)
         R.append(t)
     R1, R2, R3, R4, R5 = R
     # pyramid[level] collects the down-skip tensors landing on that decoder level
