@@ -32,6 +32,14 @@ class TcConvDesc(ctypes.Structure):
                [(n, ctypes.c_int) for n in ("ld_aux", "ld_pre", "act", "dact", "accumulate")]
 
 
+class PackJob(ctypes.Structure):
+    """Mirror of dsgan_pack_job."""
+    _fields_ = [("src", ctypes.c_ulonglong), ("dst", ctypes.c_ulonglong)] + \
+               [(n, ctypes.c_int) for n in ("O", "I", "O_pad", "I_pad", "kh", "kw")] + \
+               [(n, ctypes.c_longlong) for n in ("s_o", "s_i", "s_ky", "s_kx")] + \
+               [("block0", ctypes.c_int), ("pad_", ctypes.c_int)]
+
+
 class TcWgradDesc(ctypes.Structure):
     """Mirror of dsgan_tc_wgrad_desc."""
     _fields_ = [(n, ctypes.c_int) for n in ("N", "Hg", "Wg", "Cg", "ld_g", "Hx", "Wx", "Cx", "ld_x", "x_stride", "ntaps")] + \

@@ -390,6 +390,14 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
 // 16-byte cp.async (zero-filled outside the image), then every thread owns ONE channel pair (bf16x2 -> float2, FFMA2)
 // and slides a K-wide register window along x, so each MAC pair costs ~1.4 instructions instead of ~5.
 constexpr int T_TH = 8, T_TW = 32;
+// acc += v * w on a channel pair.  Measured on B200 (scripts/micro/ffma2_rate.cu): with three DISTINCT 64-bit operands per
+// instruction (the sliding-window pattern: a fresh input, a per-tap weight and a per-column accumulator) packed FFMA2 sustains
+// 78 FMA/clk/SM, two scalar FFMAs 104 (both 125 when the multiplicands are shared) -- so the window sweep uses scalar FFMAs.
+// (A persistent, double-buffered variant of k_dwconv_t that overlaps the staging of tile i+1 with the sweep of tile i was
+// measured at the same 0.46 ms per 16x256x256x128 pass and was not kept.)
+__device__ __forceinline__ float2 fma_pair(float2 v, float2 w, float2 acc) {
+  return make_float2(fmaf(v.x, w.x, acc.x), fmaf(v.y, w.y, acc.y));
+}
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(256) k_dwconv_t(const bf16* __restrict__ x, in
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
         const int ox = xi - kx;
-        if (ox >= 0 && ox < XW) acc[ox] = __ffma2_rn(v, wr[kx], acc[ox]);
+        if (ox >= 0 && ox < XW) acc[ox] = fma_pair(v, wr[kx], acc[ox]);
       }
     }
   }
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(320) k_dwconv_wgrad_t(const bf16* __restrict__
           const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + (size_t)xi * CB));
           // input column xi pairs with output column ox = xi - kx  ->  tap kx uses dy[xi - kx] = gw[kx]
 #pragma unroll
-          for (int kx = 0; kx < K; ++kx) acc[kx] = __ffma2_rn(v, gw[kx], acc[kx]);
+          for (int kx = 0; kx < K; ++kx) acc[kx] = fma_pair(v, gw[kx], acc[kx]);
         }
       }
     }

@@ -498,9 +498,46 @@ __global__ void k_pack_slabs(const float* __restrict__ src, bf16* __restrict__ d
     dst[idx] = __float2bfloat16_rn(v);
   }
 }
+// all conv-weight slabs of a network in ONE launch.  jobs[] lives in device memory; every block owns PACK_CHUNK consecutive
+// output elements of one job (jobs[j].block0 = first block of job j, ascending), so big and small layers get blocks in
+// proportion to their size.
+constexpr int PACK_CHUNK = 1024;
+__global__ void __launch_bounds__(256) k_pack_slabs_batched(const dsgan_pack_job* __restrict__ jobs, int njobs) {
+  __shared__ int sj;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {                       // last job whose block0 <= blockIdx.x
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    sj = lo;
+  }
+  __syncthreads();
+  const dsgan_pack_job j = jobs[sj];
+  const float* src = reinterpret_cast<const float*>(j.src);
+  bf16* dst = reinterpret_cast<bf16*>(j.dst);
+  const long long total = (long long)j.kh * j.kw * j.O_pad * j.I_pad;
+  const long long base = (long long)((int)blockIdx.x - j.block0) * PACK_CHUNK;
+#pragma unroll
+  for (int u = 0; u < PACK_CHUNK / 256; ++u) {
+    const long long idx = base + u * 256 + threadIdx.x;
+    if (idx >= total) break;
+    const int i = (int)(idx % j.I_pad);
+    const int o = (int)((idx / j.I_pad) % j.O_pad);
+    const int slab = (int)(idx / ((long long)j.I_pad * j.O_pad));
+    const int ky = slab / j.kw, kx = slab % j.kw;
+    const float v = (o < j.O && i < j.I) ? __ldg(src + o * j.s_o + i * j.s_i + ky * j.s_ky + kx * j.s_kx) : 0.f;
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
 }  // namespace
 
 extern "C" {
+int dsgan_pack_conv_weights(const dsgan_pack_job* jobs_dev, int njobs, int total_blocks, void* stream) {
+  DS_REQUIRE(jobs_dev && njobs >= 1 && total_blocks >= 1, "pack_conv_weights: bad job table");
+  k_pack_slabs_batched<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs_dev, njobs);
+  return DS_LAUNCHED("pack_conv_weights");
+}
 int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int O_pad, int I_pad, int kh, int kw,
                            long long s_o, long long s_i, long long s_ky, long long s_kx, int flip, void* stream) {
   DS_REQUIRE(O_pad >= O && I_pad >= I && I_pad % 64 == 0, "pack_conv_weight: bad padding %d>=%d %d>=%d", O_pad, O, I_pad, I);

@@ -12,7 +12,7 @@ import ctypes
 
 import torch
 
-from ._lib import ConvDesc, TcConvDesc, TcWgradDesc, lib, require_device
+from ._lib import ConvDesc, PackJob, TcConvDesc, TcWgradDesc, lib, require_device
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -85,7 +85,7 @@ class Param:
 
 
 FAMILY = {"conv_fwd": "dense", "conv_wgrad": "dense", "tc_gemm": "dense", "tc_wgrad": "dense", "tc_conv": "dense",
-          "tc_conv_wgrad": "dense", "pack_conv_weight": "optim",
+          "tc_conv_wgrad": "dense", "pack_conv_weight": "optim", "pack_conv_weights": "optim",
           "colsum": "reduce", "dwconv_fwd": "dwconv", "dwconv_wgrad": "dwconv",
           "inorm_stats": "norm", "inorm_apply": "norm", "inorm_bwd_stats": "norm", "inorm_bwd_apply": "norm",
           "maxpool_fwd": "pool", "maxpool_bwd": "pool", "ca_fwd": "ca", "ca_bwd": "ca", "scale_nc_fwd": "ca",
@@ -316,10 +316,42 @@ class Ctx:
                                     self.stream)
             ev = torch.cuda.Event()
             ev.record(cur)
-            w.cache[key] = hit = (w.epoch, buf, ev, sid, cap)
-        elif hit[3] != sid and hit[4] == cap:
+            w.cache[key] = hit = (w.epoch, buf, ev, sid, cap, (O, I, Op, Ip, k, wst))
+        elif hit[3] != sid and not cap and not hit[4]:
             cur.wait_event(hit[2])      # packed on another stream in this step (forked branch sharing the same weights)
+        # (while capturing, every slab was re-packed by repack_slabs() on the forking stream before any branch started, so
+        #  fork()'s wait_stream already orders it; events of another capture must not be waited on)
         return hit[1].data_ptr(), Op, Ip
+
+    def repack_slabs(self, tree):
+        """Re-pack every conv-weight slab a network has used so far in ONE launch (called right after the network's bf16
+        shadow was refreshed, on the stream that forks the branches): 48 tiny per-layer launches per step otherwise."""
+        entries = [(p, key) for p in tree._plist.values() for key in p.cache if isinstance(key, tuple) and key[0] == "slabs"]
+        if not entries:
+            return
+        sig = tuple((p.name, key) for p, key in entries)
+        st = tree.__dict__.get("_slab_jobs")
+        if st is None or st[0] != sig:
+            jobs = (PackJob * len(entries))()
+            nblocks = 0
+            for j, (p, key) in zip(jobs, entries):
+                O, I, Op, Ip, k, wst = p.cache[key][5]
+                j.src, j.dst = p.ptr, p.cache[key][1].data_ptr()
+                j.O, j.I, j.O_pad, j.I_pad, j.kh, j.kw = O, I, Op, Ip, k, k
+                j.s_o, j.s_i, j.s_ky, j.s_kx = wst
+                j.block0 = nblocks
+                nblocks += (k * k * Op * Ip + 1023) // 1024
+            host = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+            st = (sig, host.to(self.device), len(entries), nblocks)
+            tree.__dict__["_slab_jobs"] = st
+        cur = torch.cuda.current_stream(self.device)
+        self.L.pack_conv_weights(st[1].data_ptr(), st[2], st[3], self.stream)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        cap = torch.cuda.is_current_stream_capturing()
+        for p, key in entries:
+            old = p.cache[key]
+            p.cache[key] = (p.epoch, old[1], ev, cur.cuda_stream, cap, old[5])
 
     def _tc_conv(self, geom, xin, w, wst, bias_ptr, out, act, dact, acc, aux, pre, transposed):
         """tcgen05 implicit-GEMM path of conv_raw; returns False when the shape is not eligible."""

@@ -103,7 +103,8 @@ class ParamTree(nn.Module):
                 return
         self._sig = sig
         ctx.L.pack_bf16(flat.data_ptr(), self._flat_bf16.data_ptr(), flat.numel(), ctx.stream)
-        self.pack_epoch += 1  # conv-weight slabs cached on the Params are re-packed lazily
+        self.pack_epoch += 1  # conv-weight slabs cached on the Params: first use packs lazily, later steps in one launch
+        ctx.repack_slabs(self)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -136,9 +137,11 @@ def _upsample(ctx: Ctx, P, p, x: Var, skip: Var):
     return cat
 
 
-def _downskip(ctx: Ctx, P, name, x: Var, k):
-    """MaxPool(k) -> 1x1 (no bias) -> IN -> GELU (MixConvNeXtML.py:328-426)."""
-    return inorm(ctx, conv2d(ctx, maxpool(ctx, x, k), P[name + ".1.weight"], None, 1), act=ACT_GELU)
+def _downskip(ctx: Ctx, P, name, x: Var, k, pooled: Var = None):
+    """MaxPool(k) -> 1x1 (no bias) -> IN -> GELU (MixConvNeXtML.py:328-426).  `pooled`: MaxPool(k)(x) if the caller already
+    has it (the k = 2 branch pools the same tensor as the encoder's downSample: one kernel, gradients fan in)."""
+    px = pooled if pooled is not None else maxpool(ctx, x, k)
+    return inorm(ctx, conv2d(ctx, px, P[name + ".1.weight"], None, 1), act=ACT_GELU)
 
 
 def _midmlka(ctx: Ctx, P, p, x: Var):
@@ -180,20 +183,23 @@ def generator_forward(ctx: Ctx, P, x: Var) -> Var:
     fk = ctx.fork()          # the local (OriginMLKA) branch only shares the input with the main U-Net
     with fk:
         loc = _local(ctx, P, x)
-    R, t = [], x
+    R, pools, t = [], [], x
     for i, (name, _cin, cout) in enumerate(specs.ENC):
         out = None
         if i < 4:   # R1..R4 are the decoder's skip tensors: write them straight into channels [C, 2C) of its concat buffer
             out = ctx.new(x.N, x.H >> i, x.W >> i, 2 * cout).slice(cout, cout)
-        t = _block(ctx, P, name, t if i == 0 else maxpool(ctx, t, 2), out=out, need_dx=i > 0)
+        if i > 0:
+            t = maxpool(ctx, t, 2)
+            pools.append(t)     # MaxPool2d(2)(R_i): also the input of R_i's first down-skip branch
+        t = _block(ctx, P, name, t, out=out, need_dx=i > 0)
         R.append(t)
     R1, R2, R3, R4, R5 = R
     # pyramid[level] collects the down-skip tensors landing on that decoder level
     lvl = {16: [R5], 8: [], 4: [], 2: []}
-    for (mod, _cin, branches), src in zip(specs.SKIPS, (R1, R2, R3, R4)):
+    for (mod, _cin, branches), src, p2 in zip(specs.SKIPS, (R1, R2, R3, R4), pools):
         for br, k, _cout in branches:
             scale = (x.H // src.H) * k          # total down-sampling w.r.t. the input
-            lvl[scale].append(_downskip(ctx, P, "%s.%s" % (mod, br), src, k))
+            lvl[scale].append(_downskip(ctx, P, "%s.%s" % (mod, br), src, k, pooled=p2 if k == 2 else None))
     o = add_n(ctx, lvl[16])
     for (up, blk, _cin, _cout), skip, s in zip(specs.DEC, (R4, R3, R2, R1), (8, 4, 2, None)):
         o = _block(ctx, P, blk, _upsample(ctx, P, up + ".model.0", o, skip))

@@ -150,6 +150,17 @@ int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void*
 int dsgan_pack_conv_weight(const float* src, void* dst, int O, int I, int O_pad, int I_pad, int kh, int kw,
                            long long s_o, long long s_i, long long s_ky, long long s_kx, int flip, void* stream);
 
+/* The same packing for a whole network in one launch: jobs_dev is a DEVICE array of njobs descriptors (no flip).  Every block
+ * packs 1024 consecutive output elements of one job: block0 = first block of the job (ascending), total_blocks = their sum. */
+typedef struct {
+  unsigned long long src;  /* const float*  : master weight */
+  unsigned long long dst;  /* bf16*         : slab buffer [kh*kw][O_pad][I_pad] */
+  int O, I, O_pad, I_pad, kh, kw;
+  long long s_o, s_i, s_ky, s_kx;
+  int block0, pad_;
+} dsgan_pack_job;
+int dsgan_pack_conv_weights(const dsgan_pack_job* jobs_dev, int njobs, int total_blocks, void* stream);
+
 /* ---- depthwise convolution (MixConvNeXtML.py:94-97,220: k = 3,5,7,9, stride 1, pad k/2) ---- */
 /* flip=0: forward (w is [C,1,k,k] fp32, bias may be NULL); flip=1: input-gradient (correlate with the
  * flipped kernel, no bias). */
