@@ -49,7 +49,7 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);  // keep ~190 KB in flight
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;   // barriers (<= 33 x 8 B + TMEM slot) + base-alignment slack
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -57,17 +57,47 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN>
+// HALO variant (3x3 stride-1 layers with 64 input channels, VGG conv1_2 and its input-gradient): the generic kernel fetches
+// the input tile once per tap (nine 16 KB boxes per 128x64 output tile: ncu shows the layer L2->SM bound at 13 % tensor
+// activity).  Here a tile is 16 rows x 8 columns of pixels, ONE (16+2) x (8+2) halo is staged per tile (a single 4-D TMA box,
+// stored densely) and every tap reads it through the smem descriptor at a different start offset: 8 consecutive pixels of an
+// image row are one 8x128-byte swizzle group, SBO = one halo row (1280 B).  All tap weights stay resident in smem.
+struct HaloLayout {
+  static constexpr int ROWS = 18, COLS = 10;                             // halo rows x pixels, dense: [18][10][64 ch]
+  static constexpr int ROW_BYTES = COLS * 128;                           // 1280 B: SBO of the A descriptor (the 128-byte swizzle
+                                                                         // is a function of the absolute smem address, so
+                                                                         // neither the start nor SBO need 1024-byte alignment)
+  static constexpr int TILE_BYTES = ROWS * ROW_BYTES;                    // 23040 B delivered by ONE 4-D TMA box per tile
+  static constexpr int STAGE_BYTES = 23552;                              // next multiple of 1024
+  static constexpr int STAGES = 4;
+  static constexpr int W_BYTES = 9 * 64 * 128;                           // nine 64x64 bf16 slabs
+  static constexpr int A_OFF = W_BYTES;
+  static constexpr int BAR_OFF = A_OFF + STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+};
+
+template <int BN, bool HALO = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   using SL = SmemLayout<BN>;
+  constexpr int NSTAGE = HALO ? HaloLayout::STAGES : SL::STAGES;
+  constexpr int TILE_H = HALO ? 16 : TH, TILE_W = HALO ? 8 : TW;
+  // Epilogue teams: a 128 x BN accumulator is 4 lane quarters x BN/32 column chunks = 4*CHUNKS warp tasks.  With BN = 32 / 64
+  // that is 4 / 8 of the 16 epilogue warps, and a tile's epilogue is latency- (not throughput-) bound, so the warps are split
+  // into TEAMS that drain different tiles concurrently, and the TMEM ring is deepened to two accumulators per team.
+  constexpr int CHUNKS = BN / 32;
+  constexpr int TEAMS = CHUNKS >= 4 ? 1 : 4 / CHUNKS;                 // BN 32 -> 4, 64 -> 2, >= 128 -> 1
+  constexpr int TEAM_WARPS = EPI_WARPS / TEAMS;                       // warps arriving on an accumulator's "empty" barrier
+  constexpr int NACC = 2 * TEAMS;                                     // accumulators in TMEM (NACC * BN <= 512 columns)
+  constexpr int TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
-  uint64_t* empty = full + SL::STAGES;
-  uint64_t* tfull = empty + SL::STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (HALO ? HaloLayout::BAR_OFF : SL::BAR_OFF));
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* tfull = empty + NSTAGE;
+  uint64_t* tempty = tfull + NACC;
+  uint64_t* wfull = tempty + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_y * p.tiles_x;
@@ -77,11 +107,12 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < SL::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TEAM_WARPS); }
+    mbar_init(wfull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -90,7 +121,20 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (HALO) {   // all tap weights once, then one halo per tile
+        mbar_expect_tx(wfull, (uint32_t)p.ntaps[0] * BN * 128);
+        for (int t = 0; t < p.ntaps[0]; ++t) tma_load_2d(smem + t * BN * 128, &tmB, wfull, 0, p.slab[t] * p.co_pad);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          const int img = tile / tiles_per_img, t2 = tile % tiles_per_img;
+          const int y0 = (t2 / p.tiles_x) * TILE_H, x0 = (t2 % p.tiles_x) * TILE_W;
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + HaloLayout::A_OFF + stage * HaloLayout::STAGE_BYTES;
+          mbar_expect_tx(&full[stage], HaloLayout::TILE_BYTES);
+          tma_load_4d(sa, &tmA, &full[stage], 0, x0 - 1, y0 - 1, img);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        }
+      }
+      for (int tile = blockIdx.x; !HALO && tile < num_tiles; tile += gridDim.x) {
         const int n_blk = tile % p.n_tiles;
         const int cls = (tile / p.n_tiles) % p.nclass;
         const int sp = tile / (p.n_tiles * p.nclass);
@@ -104,7 +148,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             mbar_expect_tx(&full[stage], SL::STAGE_BYTES);
             tma_load_4d(sa, &tmA, &full[stage], c * BK, cx, cy, img);
             tma_load_2d(sa + SL::A_BYTES, &tmB, &full[stage], c * BK, p.slab[t] * p.co_pad + n_blk * BN);
-            if (++stage == SL::STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -114,7 +158,39 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       constexpr uint32_t IDESC = idesc_bf16(BM, BN, false, false);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (HALO) {
+        // tap (dy, dx): the 16x8 pixel window starts at halo row 1+dy, pixel 1+dx.  The nine start offsets are tile-invariant:
+        // keep them (in the descriptor's 16-byte units) in registers so that the issuing thread does nothing per tile but
+        // wait, add and issue 36 MMAs (it, not the tensor pipe, was the bottleneck of this layer).
+        uint32_t aoff[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+          aoff[t] = (uint32_t)((1 + p.dy[t]) * HaloLayout::ROW_BYTES + (1 + p.dx[t]) * 128) >> 4;
+        mbar_wait(wfull, 0);
+        tc_fence_after();
+        const uint64_t bdesc0 = smem_desc_sw128(smem_u32(smem), 16, 1024);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BN;
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc0 =
+              smem_desc_sw128(smem_u32(smem + HaloLayout::A_OFF + stage * HaloLayout::STAGE_BYTES), 16, HaloLayout::ROW_BYTES);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(d_tmem, adesc0 + (uint64_t)(aoff[t] + k * 2), bdesc0 + (uint64_t)(t * (BN * 128 >> 4) + k * 2), IDESC,
+                        (t > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          umma_commit(&tfull[acc]);
+          if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+      for (int tile = blockIdx.x; !HALO && tile < num_tiles; tile += gridDim.x) {
         const int nk = p.ntaps[(tile / p.n_tiles) % p.nclass] * kc;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -129,23 +205,27 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), IDESC, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
-          if (++stage == SL::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     const int quarter = warp & 3;
-    const int part = (warp - 2) >> 2, nparts = EPI_WARPS / 4;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int part = (warp - 2) >> 2;                          // 0..3
+    const int team = CHUNKS >= 4 ? 0 : part / CHUNKS;           // which tiles this warp drains: team, team + TEAMS, ...
+    const int c_first = CHUNKS >= 4 ? part : part % CHUNKS, c_step = CHUNKS >= 4 ? 4 : CHUNKS;
+    int it = team;                                              // index of the tile in this CTA's sequence
+    for (int tile = blockIdx.x + team * gridDim.x; tile < num_tiles; tile += TEAMS * gridDim.x, it += TEAMS) {
+      const int acc = it % NACC;
+      const uint32_t acc_phase = (uint32_t)(it / NACC) & 1u;
       const int n_blk = tile % p.n_tiles;
       const int cls = (tile / p.n_tiles) % p.nclass;
       const int sp = tile / (p.n_tiles * p.nclass);
       const int img = sp / tiles_per_img, t2 = sp % tiles_per_img;
       const int r = quarter * 32 + lane;
-      const int gy = (t2 / p.tiles_x) * TH + r / TW, gx = (t2 % p.tiles_x) * TW + r % TW;
+      const int gy = (t2 / p.tiles_x) * TILE_H + r / TILE_W, gx = (t2 % p.tiles_x) * TILE_W + r % TILE_W;
       const int oy = gy * p.os_ + p.oy0[cls], ox = gx * p.os_ + p.ox0[cls];
       const bool row_ok = gy < p.Hg && gx < p.Wg && oy < p.Ho && ox < p.Wo;
       const size_t pix = ((size_t)img * p.Ho + oy) * p.Wo + ox;
@@ -157,7 +237,7 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = part; c < BN / 32; c += nparts) {
+      for (int c = c_first; c < CHUNKS; c += c_step) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
@@ -253,14 +333,13 @@ k_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -435,6 +514,20 @@ struct Key2 {
 std::map<Key2, CUtensorMap> g_maps2;
 std::mutex g_mu;
 
+// halo of the HALO variant: box {64 channels, 10 pixels, 18 rows, 1 image}
+int map_input_halo(CUtensorMap* out, const void* base, int N, int H, int W, int C, int ld) {
+  Key4 k{base, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)ld, 0x7a10u};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps4.find(k);
+  if (it != g_maps4.end()) { *out = it->second; return 0; }
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  uint32_t box[4] = {64, (uint32_t)HaloLayout::COLS, (uint32_t)HaloLayout::ROWS, 1};
+  if (encode_tmap_bf16(out, base, 4, dims, strides, box, nullptr)) return 1;
+  if (g_maps4.size() > 4096) g_maps4.clear();
+  g_maps4[k] = *out;
+  return 0;
+}
 int map_input(CUtensorMap* out, const void* base, int N, int H, int W, int C, int ld, int es) {
   Key4 k{base, (uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)ld, (uint32_t)es};
   std::lock_guard<std::mutex> lk(g_mu);
@@ -481,6 +574,20 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cuda
   const int grid = tiles < sms() ? (int)tiles : sms();
   k_tc_conv<BN><<<grid, NUM_THREADS, smem, s>>>(a, b, p);
   return DS_LAUNCHED("tc_conv");
+}
+
+int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
+  static bool attr = false;
+  constexpr int smem = HaloLayout::TOTAL;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("tc_conv(halo) smem attr: %s", cudaGetErrorString(e)); return 1; }
+    attr = true;
+  }
+  const long long tiles = (long long)p.N * p.tiles_y * p.tiles_x;
+  const int grid = tiles < sms() ? (int)tiles : sms();
+  k_tc_conv<64, true><<<grid, NUM_THREADS, smem, s>>>(a, b, p);
+  return DS_LAUNCHED("tc_conv_halo");
 }
 
 // dst[slab][o][i] (bf16) = src[o*so + i*si + tap_offset(slab)]  — packs OIHW / IOHW fp32 weights into K-major slabs
@@ -570,6 +677,24 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
     if (sc::conv_try(d, in, w_slabs, bias, out, pre_out, aux, stream, &rc)) return rc;
   }
   const int BN = d->Co >= 256 ? 256 : (d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32));
+  // 3x3 / stride 1 / 64 -> 64 channels: halo-staged variant (taps read one staged halo at different descriptor offsets)
+  bool halo = d->Ci == 64 && d->Co == 64 && d->co_pad == 64 && d->ci_pad == 64 && d->nclass == 1 &&
+              d->in_stride == 1 && d->out_stride == 1 && d->ntaps[0] == 9 && d->oy0[0] == 0 && d->ox0[0] == 0;
+  for (int t = 0; halo && t < d->ntaps[0]; ++t) halo = d->dy[t] >= -1 && d->dy[t] <= 1 && d->dx[t] >= -1 && d->dx[t] <= 1;
+  if (halo) {
+    CUtensorMap ta, tb;
+    if (map_input_halo(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in)) return 1;
+    if (map_weight(&tb, w_slabs, d->ci_pad, d->nslabs * d->co_pad, 64)) return 1;
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Ci = d->Ci; p.Co = d->Co; p.co_pad = d->co_pad;
+    p.is_ = 1; p.os_ = 1; p.Ho = d->Ho; p.Wo = d->Wo; p.nclass = 1; p.ntaps[0] = d->ntaps[0];
+    for (int t = 0; t < d->ntaps[0]; ++t) { p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.slab[t] = d->slab[t]; }
+    p.tiles_y = (d->Hg + 15) / 16; p.tiles_x = (d->Wg + 7) / 8; p.n_tiles = 1;
+    p.C = out; p.ldc = d->ld_out; p.bias = bias; p.pre = pre_out; p.ld_pre = d->ld_pre; p.aux = aux; p.ld_aux = d->ld_aux;
+    p.act = d->act; p.dact = d->dact; p.accumulate = d->accumulate;
+    return launch_halo(ta, tb, p, (cudaStream_t)stream);
+  }
   CUtensorMap ta, tb;
   if (map_input(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in, d->in_stride)) return 1;
   if (map_weight(&tb, w_slabs, d->ci_pad, d->nslabs * d->co_pad, BN)) return 1;

@@ -86,7 +86,7 @@ struct SmemLayout {
   // the ring is latency-bound (TMA round trip ~1-2 us): keep ~190 KB in flight -> 8 / 6 / 4 stages for BN = 64 / 128 / 256
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for 1024-B alignment
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;  // barriers + slack for 1024-B alignment
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -100,13 +100,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   constexpr bool A_MN = (MODE == 2), B_MN = (MODE >= 1);
   using SL = SmemLayout<BN>;
+  // Epilogue teams (see tc_conv.cu): a 128 x BN accumulator is 4*BN/32 warp tasks; with BN = 64 the 16 epilogue warps split
+  // into two teams that drain different tiles concurrently, the TMEM ring holds two accumulators per team.
+  constexpr int CHUNKS = BN / 32;
+  constexpr int TEAMS = CHUNKS >= 4 ? 1 : 4 / CHUNKS;
+  constexpr int TEAM_WARPS = EPI_WARPS / TEAMS;
+  constexpr int NACC = 2 * TEAMS;
+  constexpr int TMEM_COLS = NACC * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SL::BAR_OFF);
   uint64_t* empty = full + SL::STAGES;
   uint64_t* tfull = empty + SL::STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + NACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles * p.splits;
@@ -115,10 +122,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < SL::STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], EPI_WARPS); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TEAM_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -184,15 +191,19 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           if (++stage == SL::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[acc]);      // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // ================= epilogue warps (2..5): TMEM -> registers -> global =================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int part = (warp - 2) >> 2, nparts = EPI_WARPS / 4;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int part = (warp - 2) >> 2;
+    const int team = CHUNKS >= 4 ? 0 : part / CHUNKS;
+    const int c_first = CHUNKS >= 4 ? part : part % CHUNKS, c_step = CHUNKS >= 4 ? 4 : CHUNKS;
+    int it = team;
+    for (int tile = blockIdx.x + team * gridDim.x; tile < num_tiles; tile += TEAMS * gridDim.x, it += TEAMS) {
+      const int acc = it % NACC;
+      const uint32_t acc_phase = (uint32_t)(it / NACC) & 1u;
       const int n_blk = tile % p.n_tiles, m_blk = (tile / p.n_tiles) % p.m_tiles;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -203,7 +214,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         (!p.pre || (p.ld_pre % 16 == 0 && (uintptr_t)p.pre % 32 == 0)) &&
                         (!p.aux || (p.ld_aux % 16 == 0 && (uintptr_t)p.aux % 32 == 0));
 #pragma unroll 1
-      for (int c = part; c < BN / 32; c += nparts) {
+      for (int c = c_first; c < CHUNKS; c += c_step) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
@@ -290,7 +301,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   // ---- teardown ----
@@ -298,7 +308,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
