@@ -576,17 +576,18 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cuda
   return DS_LAUNCHED("tc_conv");
 }
 
+template <int BN>
 int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const ConvParams& p, cudaStream_t s) {
   static bool attr = false;
   constexpr int smem = HaloLayout::TOTAL;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k_tc_conv<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("tc_conv(halo) smem attr: %s", cudaGetErrorString(e)); return 1; }
     attr = true;
   }
   const long long tiles = (long long)p.N * p.tiles_y * p.tiles_x;
   const int grid = tiles < sms() ? (int)tiles : sms();
-  k_tc_conv<64, true><<<grid, NUM_THREADS, smem, s>>>(a, b, p);
+  k_tc_conv<BN, true><<<grid, NUM_THREADS, smem, s>>>(a, b, p);
   return DS_LAUNCHED("tc_conv_halo");
 }
 
@@ -672,19 +673,16 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
   DS_REQUIRE(((uintptr_t)in % 16 == 0) && ((uintptr_t)w_slabs % 16 == 0), "tc_conv: unaligned");
   DS_REQUIRE(d->ci_pad % 64 == 0 && d->ci_pad >= d->Ci && d->co_pad >= d->Co, "tc_conv: bad slab padding");
   DS_REQUIRE(!d->dact || aux, "tc_conv: dact needs aux");
-  {
-    int rc = 0;   // 1/3/6/12-channel layers: CUDA-core direct convolution (sc_conv.cu), same contract
-    if (sc::conv_try(d, in, w_slabs, bias, out, pre_out, aux, stream, &rc)) return rc;
-  }
-  const int BN = d->Co >= 256 ? 256 : (d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32));
-  // 3x3 / stride 1 / 64 -> 64 channels: halo-staged variant (taps read one staged halo at different descriptor offsets)
-  bool halo = d->Ci == 64 && d->Co == 64 && d->co_pad == 64 && d->ci_pad == 64 && d->nclass == 1 &&
-              d->in_stride == 1 && d->out_stride == 1 && d->ntaps[0] == 9 && d->oy0[0] == 0 && d->ox0[0] == 0;
+  // 3x3 / stride 1 / 64 input channels / <= 64 output channels (VGG conv1_2 and its input-gradient, the generator's 64 -> 3
+  // `res` conv, VGG conv1_1's input-gradient): halo-staged variant (taps read one staged halo at different descriptor offsets)
+  bool halo = d->Ci == 64 && d->ci_pad == 64 && ((d->Co == 64 && d->co_pad == 64) || (d->Co <= 32 && d->co_pad == 32)) &&
+              d->nclass == 1 && d->in_stride == 1 && d->out_stride == 1 && d->ntaps[0] == 9 && d->oy0[0] == 0 &&
+              d->ox0[0] == 0;
   for (int t = 0; halo && t < d->ntaps[0]; ++t) halo = d->dy[t] >= -1 && d->dy[t] <= 1 && d->dx[t] >= -1 && d->dx[t] <= 1;
   if (halo) {
     CUtensorMap ta, tb;
     if (map_input_halo(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in)) return 1;
-    if (map_weight(&tb, w_slabs, d->ci_pad, d->nslabs * d->co_pad, 64)) return 1;
+    if (map_weight(&tb, w_slabs, d->ci_pad, d->nslabs * d->co_pad, d->co_pad)) return 1;
     ConvParams p;
     memset(&p, 0, sizeof(p));
     p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Ci = d->Ci; p.Co = d->Co; p.co_pad = d->co_pad;
@@ -693,8 +691,13 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
     p.tiles_y = (d->Hg + 15) / 16; p.tiles_x = (d->Wg + 7) / 8; p.n_tiles = 1;
     p.C = out; p.ldc = d->ld_out; p.bias = bias; p.pre = pre_out; p.ld_pre = d->ld_pre; p.aux = aux; p.ld_aux = d->ld_aux;
     p.act = d->act; p.dact = d->dact; p.accumulate = d->accumulate;
-    return launch_halo(ta, tb, p, (cudaStream_t)stream);
+    return d->co_pad == 64 ? launch_halo<64>(ta, tb, p, (cudaStream_t)stream) : launch_halo<32>(ta, tb, p, (cudaStream_t)stream);
   }
+  {
+    int rc = 0;   // 1/3/6/12-channel layers: CUDA-core direct convolution (sc_conv.cu), same contract
+    if (sc::conv_try(d, in, w_slabs, bias, out, pre_out, aux, stream, &rc)) return rc;
+  }
+  const int BN = d->Co >= 256 ? 256 : (d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32));
   CUtensorMap ta, tb;
   if (map_input(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in, d->in_stride)) return 1;
   if (map_weight(&tb, w_slabs, d->ci_pad, d->nslabs * d->co_pad, BN)) return 1;
