@@ -104,6 +104,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 // 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  In the epilogues every lane owns one output ROW, so a warp's store
 // touches 32 different rows: with 16-byte stores each 32-byte sector is written in two halves by two instructions (ncu:
 // 134 M sector writes for 2.1 GB); one 32-byte store per lane writes whole sectors.  `p` must be 32-byte aligned.
@@ -127,6 +137,22 @@ __device__ __forceinline__ void store_row32(void* p, const float (&f)[32]) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) w[e] = bf16x2_bits(f[q * 16 + 2 * e], f[q * 16 + 2 * e + 1]);
     st_global_v8(reinterpret_cast<uint8_t*>(p) + q * 32, w);
+  }
+}
+// 16 fp32 values <-> 32 bytes of bf16 (one 256-bit access)
+__device__ __forceinline__ void store_row16(void* p, const float (&f)[16]) {
+  uint32_t w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = bf16x2_bits(f[2 * e], f[2 * e + 1]);
+  st_global_v8(p, w);
+}
+__device__ __forceinline__ void load_row16(const void* p, float (&a)[16]) {
+  uint32_t w[8];
+  ld_global_v8(p, w);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[2 * e] = __uint_as_float(w[e] << 16);
+    a[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
   }
 }
 // 64 bytes of bf16 at p -> 32 fp32 values

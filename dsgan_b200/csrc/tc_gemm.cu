@@ -86,8 +86,10 @@ struct SmemLayout {
   // the ring is latency-bound (TMA round trip ~1-2 us): keep ~190 KB in flight -> 8 / 6 / 4 stages for BN = 64 / 128 / 256
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 512 + 1024;  // barriers + slack for 1024-B alignment
+  static constexpr int BIAS_OFF = BAR_OFF + 512;       // fp32 bias vector (N <= MAX_SMEM_BIAS), read by every tile's epilogue
+  static constexpr int TOTAL = BIAS_OFF + 4 * 4096 + 1024;  // barriers + bias + slack for 1024-B alignment
 };
+constexpr int MAX_SMEM_BIAS = 4096;
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -126,6 +128,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  // the bias is the same for every tile with the same column block: keep it in shared memory (a global load per 32-column
+  // chunk sat on the epilogue's critical path: 11 % of uc4.pwconv1)
+  float* sbias = reinterpret_cast<float*>(smem + SL::BIAS_OFF);
+  const bool bias_smem = MODE != 2 && p.bias != nullptr && p.N <= MAX_SMEM_BIAS;
+  if (bias_smem)
+    for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) sbias[i] = __ldg(p.bias + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -230,10 +238,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+            const float4* bp = reinterpret_cast<const float4*>((bias_smem ? sbias : p.bias) + col0);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const float4 b4 = __ldg(bp + q);
+              const float4 b4 = bp[q];
               f[q * 4] += b4.x; f[q * 4 + 1] += b4.y; f[q * 4 + 2] += b4.z; f[q * 4 + 3] += b4.w;
             }
           }
