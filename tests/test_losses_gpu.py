@@ -117,3 +117,24 @@ def test_ssim_identity_and_errors():
         K.ms_ssim(X[:, :, :160, :160].contiguous(), X[:, :, :160, :160].contiguous(), data_range=1)
     with pytest.raises(ValueError):
         K.ssim(X, X, data_range=1, win_size=10)
+
+
+def test_ms_ssim_full_size_properties():
+    """BASELINE configs[3] size (64 x 3 x 256 x 256): size-independent properties, plus the CPU oracle on a 2-image slice."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.rand(64, 3, 256, 256, device="cuda", generator=g)
+    Y = (X + 0.1 * torch.randn(X.shape, device="cuda", generator=g)).clamp(0, 1)
+    for fn, tol in ((K.ms_ssim, 1e-4), (K.ssim, 1e-5)):
+        per = fn(X, Y, data_range=1, size_average=False)
+        assert per.shape == (64,)
+        sub = fn(X[8:12].contiguous(), Y[8:12].contiguous(), data_range=1, size_average=False)
+        assert torch.allclose(per[8:12], sub, atol=1e-6)                       # images are independent
+        assert abs(float(fn(X, Y, data_range=1)) - float(per.mean())) < 1e-5   # the mean is the mean of the per-image values
+        assert float((fn(X, X, data_range=1, size_average=False) - 1).abs().max()) < tol   # identity
+        Yc = Y.clone().requires_grad_(True)
+        fn(X, Yc, data_range=1).backward()
+        Ys = Y[8:12].clone().requires_grad_(True)
+        fn(X[8:12].contiguous(), Ys, data_range=1).backward()
+        assert rel(Yc.grad[8:12].cpu() * 16, Ys.grad.cpu()) < 1e-4            # d mean / dY of a slice, rescaled 64/4
+        ref = getattr(O, fn.__name__)(X[:2].cpu(), Y[:2].cpu(), 1.0, size_average=False)
+        assert torch.allclose(per[:2].cpu(), ref, atol=5e-5)
