@@ -129,6 +129,20 @@ class Pix2PixModel(BaseModel):
         dfake = torch.empty_like(fake)
         ctx.zero_(dfake)
         ctx.param_grads = False  # D and VGG are frozen here (set_requires_grad(netD, False), vgg.py:27-28)
+        # VGG(real_B) needs nothing from this step: run it (no tape) on the side stream, next to the discriminator's small
+        # kernels; joined right before the feature losses.
+        side = None
+        if ctx.use_streams and fake.is_cuda:
+            main = torch.cuda.current_stream(ctx.device)
+            if ctx._side_stream is None:
+                ctx._side_stream = torch.cuda.Stream(ctx.device)
+            side = ctx._side_stream
+            Pv = self.vgg.params()   # on the MAIN stream: lazy flattening / operand refresh must be ordered before both passes
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ctx.no_grad = True
+                fr = nets.vgg_forward(ctx, Pv, image_to_nhwc(ctx, real), need_dx=False)
+                ctx.no_grad = False
         if self.use_gan == 1:
             x = self._pair(self.real_A, fake) if self.use_condition == 1 else image_to_nhwc(ctx, fake)
             pred = self.netD.forward_var(x, need_dx=True)
@@ -138,11 +152,14 @@ class Pix2PixModel(BaseModel):
             nhwc_grad_to_image(ctx, gv, dfake)
         losses.l1_images(ctx, fake, real, self._slot("G_L1"), 1.0, dfake)
         # VGG perceptual loss on raw [-1,1] images (pix2pix_model.py:180-186, Q14)
-        ctx.no_grad = True
-        fr = self.vgg.forward_var(image_to_nhwc(ctx, real), need_dx=False)
-        ctx.no_grad = False
+        if side is None:
+            ctx.no_grad = True
+            fr = self.vgg.forward_var(image_to_nhwc(ctx, real), need_dx=False)
+            ctx.no_grad = False
         xv = image_to_nhwc(ctx, fake)
         ff = self.vgg.forward_var(xv, need_dx=True)
+        if side is not None:
+            torch.cuda.current_stream(ctx.device).wait_stream(side)
         for f, r in zip(ff, fr):
             losses.l1_features(ctx, f, r, self._slot("vgg"), float(self.w_vgg))
         ctx.backward()
