@@ -115,7 +115,13 @@ int dsgan_pack_bf16(const float* src, void* dst, long long n, void* stream);
  * (dsgan_pack_conv_weight).  Any Ci/Co: the input pixel pitch must be a multiple of 8 elements (TMA zero-fills the
  * channels >= Ci), narrow outputs (Co = 1, 3, 6 ...) take a scalar epilogue.
  * Covers nn.Conv2d s1/s2 and nn.ConvTranspose2d(s2) forward and input-gradients: models/vgg.py:16-25,
- * networks.py:544-569, MixConvNeXtML.py:53,150.  Epilogue as dsgan_conv_fwd. */
+ * networks.py:544-569, MixConvNeXtML.py:53,150.  Epilogue as dsgan_conv_fwd.
+ * Back ends behind this one entry point (chosen by shape, same results): the generic tcgen05 implicit GEMM; a halo-staged
+ * tcgen05 variant for 3x3 / stride-1 layers with 64 input and <= 64 output channels (vgg.py:17 conv1_2, MixConvNeXtML.py:459
+ * `res`); and a CUDA-core FFMA2 direct convolution (csrc/sc_conv.cu) for layers with 1/3/6/12 input channels or <= 16 output
+ * channels (vgg.py:16 conv1_1, networks.py:544 PatchGAN conv1, MixConvNeXtML.py:222-226 block c1).  With a ragged Co (not a
+ * multiple of 8) the CUDA-core back end writes whole 16-byte vectors: out / pre_out must then be whole-pitch tensors
+ * (ld == ceil8(Co)) whose extra lanes are padding. */
 typedef struct {
   int N, Hi, Wi, Ci, ld_in;
   int Ho, Wo, Co, ld_out;
