@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
   }
 }
 
-__global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256, 4) k_in_bwd_stats_v8(const bf16* __restrict__ x, int ldx,
                                                           const float* __restrict__ stats, const bf16* __restrict__ res,
                                                           int ldr, const bf16* __restrict__ dy, int lddy, long long HW,
                                                           int C, int act, float* __restrict__ bst, int VCHUNK) {
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(256) k_in_bwd_stats_v8(const bf16* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) k_in_bwd_apply_v8(const bf16* __restrict__ x, int ldx,
+__global__ void __launch_bounds__(256, 3) k_in_bwd_apply_v8(const bf16* __restrict__ x, int ldx,
                                                           const float* __restrict__ stats, const bf16* __restrict__ res,
                                                           int ldr, const bf16* __restrict__ dy, int lddy,
                                                           const float* __restrict__ bst, bf16* __restrict__ dx, int lddx,
