@@ -120,6 +120,71 @@ __device__ __forceinline__ uint4 pk8(const float (&f)[8]) {
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
+// CA gate (y = x * s[n,c]) and its backward, 8 channels per thread
+__global__ void k_scale_nc_fwd_v8(const bf16* __restrict__ x, const float* __restrict__ s, bf16* __restrict__ y, long long HW,
+                                  int C, long long total8) {
+  const int G = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / G;
+    const int c0 = (int)(i - pix * G) * 8;
+    const long long n = pix / HW;
+    float v[8];
+    up8(__ldg(reinterpret_cast<const uint4*>(x + i * 8)), v);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(s + n * C + c0)), s1 = __ldg(reinterpret_cast<const float4*>(s + n * C + c0 + 4));
+    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    *reinterpret_cast<uint4*>(y + i * 8) = pk8(v);
+  }
+}
+// ds[n,c] += sum_p x*dy.  grid (pixel chunks, N, channel blocks of <= 256)
+__global__ void __launch_bounds__(256) k_scale_nc_bwd_reduce_v8(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                                 float* __restrict__ ds, long long HW, int C, int chunk) {
+  __shared__ float sacc[256];
+  const int groups = C / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;
+  const int tg = threadIdx.x % gl, tp = threadIdx.x / gl;
+  const int n = blockIdx.y, cb = blockIdx.z * gl * 8, c0 = cb + tg * 8;
+  sacc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long long p0 = (long long)blockIdx.x * chunk, p1 = min(p0 + (long long)chunk, HW);
+  if (tp < pl && c0 < C) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t base = (size_t)n * HW * C + c0;
+#pragma unroll 4
+    for (long long p = p0 + tp; p < p1; p += pl) {
+      float xv[8], gv[8];
+      up8(__ldg(reinterpret_cast<const uint4*>(x + base + p * C)), xv);
+      up8(__ldg(reinterpret_cast<const uint4*>(dy + base + p * C)), gv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = fmaf(xv[e], gv[e], a[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&sacc[tg * 8 + e], a[e]);
+  }
+  __syncthreads();
+  if (threadIdx.x < gl * 8 && cb + threadIdx.x < C) atomicAdd(ds + (long long)n * C + cb + threadIdx.x, sacc[threadIdx.x]);
+}
+__global__ void k_scale_nc_bwd_apply_v8(const bf16* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ davg,
+                                        const float* __restrict__ dmax, const int* __restrict__ amax, bf16* __restrict__ dx,
+                                        long long HW, int C, int acc, long long total8) {
+  const int G = C / 8;
+  const float inv = 1.0f / (float)HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / G;
+    const int c0 = (int)(i - pix * G) * 8;
+    const long long n = pix / HW;
+    const int p = (int)(pix - n * HW);
+    const long long nc = n * C + c0;
+    float g[8], o[8];
+    up8(__ldg(reinterpret_cast<const uint4*>(dy + i * 8)), g);
+    if (acc) up8(*reinterpret_cast<const uint4*>(dx + i * 8), o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = fmaf(g[e], __ldg(s + nc + e), __ldg(davg + nc + e) * inv) + (__ldg(amax + nc + e) == p ? __ldg(dmax + nc + e) : 0.f);
+      if (acc) v += o[e];
+      g[e] = v;
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pk8(g);
+  }
+}
 __global__ void k_copy_channels_v8(const bf16* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd, long long npix,
                                    int G, int acc) {
   const long long total = npix * G;
@@ -205,6 +270,10 @@ int dsgan_add_n(void* out, int dtype, long long n, const void* a, const void* b,
 }
 int dsgan_scale_nc_fwd(const void* x, const float* s, void* y, int dtype, int N, long long HW, int C, void* stream) {
   long long total = (long long)N * HW * C;
+  if (dtype == DT_BF16 && C % 8 == 0 && (((uintptr_t)x | (uintptr_t)y | (uintptr_t)s) % 16 == 0)) {
+    k_scale_nc_fwd_v8<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, s, (bf16*)y, HW, C, total / 8);
+    return DS_LAUNCHED("scale_nc_fwd_v8");
+  }
   DS_DISPATCH_DT(dtype, (k_scale_nc_fwd<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)x, s, (T*)y, HW, C, total)));
   return DS_LAUNCHED("scale_nc_fwd");
@@ -212,6 +281,15 @@ int dsgan_scale_nc_fwd(const void* x, const float* s, void* y, int dtype, int N,
 int dsgan_scale_nc_bwd_reduce(const void* x, const void* dy, float* ds, int dtype, int N, long long HW, int C,
                               void* stream) {
   cudaMemsetAsync(ds, 0, sizeof(float) * N * C, (cudaStream_t)stream);
+  if (dtype == DT_BF16 && C % 8 == 0 && (((uintptr_t)x | (uintptr_t)dy) % 16 == 0)) {
+    const int groups = C / 8, gl = groups < 32 ? groups : 32, pl = 256 / gl;
+    const int cblocks = (C + gl * 8 - 1) / (gl * 8);
+    int ch = 2048;
+    while (ch > 4 * pl && ((HW + ch - 1) / ch) * N * cblocks < 296) ch >>= 1;
+    dim3 g8(cdiv(HW, ch), N, cblocks);
+    k_scale_nc_bwd_reduce_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, ds, HW, C, ch);
+    return DS_LAUNCHED("scale_nc_bwd_reduce_v8");
+  }
   int chunk = 256;
   dim3 grid(cdiv(HW, chunk), N);
   DS_DISPATCH_DT(dtype, (k_scale_nc_bwd_reduce<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)dy,
@@ -221,6 +299,11 @@ int dsgan_scale_nc_bwd_reduce(const void* x, const void* dy, float* ds, int dtyp
 int dsgan_scale_nc_bwd_apply(const void* dy, const float* s, const float* davg, const float* dmax, const int* argmax,
                              void* dx, int dtype, int N, long long HW, int C, int accumulate, void* stream) {
   long long total = (long long)N * HW * C;
+  if (dtype == DT_BF16 && C % 8 == 0 && (((uintptr_t)dy | (uintptr_t)dx) % 16 == 0)) {
+    k_scale_nc_bwd_apply_v8<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dy, s, davg, dmax, argmax, (bf16*)dx, HW, C, accumulate, total / 8);
+    return DS_LAUNCHED("scale_nc_bwd_apply_v8");
+  }
   DS_DISPATCH_DT(dtype, (k_scale_nc_bwd_apply<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)dy, s, davg, dmax, argmax, (T*)dx, HW, C, accumulate, total)));
   return DS_LAUNCHED("scale_nc_bwd_apply");
