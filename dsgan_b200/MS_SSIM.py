@@ -48,6 +48,11 @@ class _SSIMFn(torch.autograd.Function):
         val = torch.zeros(1, dtype=torch.float32, device=X.device)
         sums = torch.empty((levels, N * C, 2), dtype=torch.float32, device=X.device)
         need = Y.requires_grad
+        if X.requires_grad:
+            raise NotImplementedError("gradient w.r.t. X is not provided (the training call differentiates Y only, "
+                                      "pix2pix_model.py:193-195); pass X.detach()")
+        if need and not size_average:
+            raise NotImplementedError("per-image (size_average=False) gradients are not provided")
         dY = torch.zeros_like(Y) if need else None
         ssim_value_and_grad(ctx, X, Y, val.data_ptr(), 1.0, dY, 1.0, float(data_range), K, multiscale, per_plane=sums)
         fctx.dY, fctx.size_average = dY, size_average

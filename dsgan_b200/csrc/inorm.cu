@@ -105,7 +105,8 @@ template <typename T>
 __global__ void k_in_bwd_apply(const T* __restrict__ x, int ldx, const float* __restrict__ stats,
                                const T* __restrict__ res, int ldr, const T* __restrict__ dy, int lddy,
                                const float* __restrict__ bst, T* __restrict__ dx, int lddx, int acc_dx,
-                               T* __restrict__ dres, int lddr, int acc_dres, long long HW, int C, int act) {
+                               T* __restrict__ dres, int lddr, int acc_dres, long long HW, int C, int act,
+                               float* __restrict__ dbias, float* __restrict__ dsum_nc) {
   const Lanes l = lanes(C);
   if (l.tp >= l.pl) return;
   const int n = blockIdx.y;
@@ -116,6 +117,7 @@ __global__ void k_in_bwd_apply(const T* __restrict__ x, int ldx, const float* __
     float mean, rstd;
     mean_rstd(stats + ((long long)n * C + c) * 3, inv, mean, rstd);
     const float mg = bst[((long long)n * C + c) * 2] * inv, mgx = bst[((long long)n * C + c) * 2 + 1] * inv;
+    float vsum = 0.f;
     for (long long p = p0 + l.tp; p < p1; p += l.pl) {
       const float xh = (ldf(x + (base + p) * ldx + c) - mean) * rstd;
       float g = ldf(dy + (base + p) * lddy + c);
@@ -125,6 +127,7 @@ __global__ void k_in_bwd_apply(const T* __restrict__ x, int ldx, const float* __
         g *= act_bwd(act, u);
       }
       float v = rstd * (g - mg - xh * mgx);
+      vsum += v;
       T* o = dx + (base + p) * lddx + c;
       if (acc_dx) v += ldf(o);
       stf(o, v);
@@ -133,6 +136,8 @@ __global__ void k_in_bwd_apply(const T* __restrict__ x, int ldx, const float* __
         stf(r, acc_dres ? g + ldf(r) : g);
       }
     }
+    if (dbias) atomicAdd(dbias + c, vsum);
+    if (dsum_nc) atomicAdd(dsum_nc + (long long)n * C + c, vsum);
   }
 }
 
@@ -311,21 +316,33 @@ __global__ void __launch_bounds__(256, 4) k_in_bwd_stats_v8(const bf16* __restri
   }
 }
 
+// SUMS: additionally accumulate the per-(n, c) sum of the fp32 dx values BEFORE they are rounded to bf16 (and before any
+// fan-in add).  A bias that feeds an InstanceNorm has the gradient sum_p dx[p] = 0 in exact arithmetic; summing the rounded bf16
+// tensor afterwards (the old colsum pass) turned that structural zero into rounding noise of the size of a real gradient.
+template <bool SUMS>
 __global__ void __launch_bounds__(256, 3) k_in_bwd_apply_v8(const bf16* __restrict__ x, int ldx,
                                                           const float* __restrict__ stats, const bf16* __restrict__ res,
                                                           int ldr, const bf16* __restrict__ dy, int lddy,
                                                           const float* __restrict__ bst, bf16* __restrict__ dx, int lddx,
                                                           int acc_dx, bf16* __restrict__ dres, int lddr, int acc_dres,
-                                                          long long HW, int C, int act, int VCHUNK) {
+                                                          long long HW, int C, int act, int VCHUNK,
+                                                          float* __restrict__ dbias, float* __restrict__ dsum_nc) {
+  __shared__ float sacc[SUMS ? 256 : 1];
   const VLanes l = vlanes(C);
-  if (l.tp >= l.pl) return;
+  if (SUMS) {
+    sacc[threadIdx.x] = 0.f;
+    __syncthreads();
+  }
+  if (!SUMS && l.tp >= l.pl) return;
   const int n = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * VCHUNK, p1 = min(p0 + (long long)VCHUNK, HW);
   const size_t base = (size_t)n * HW;
   const float inv = 1.0f / (float)HW;
-  for (int c0 = blockIdx.z * l.gl * 8 + l.tg * 8; c0 < min(C, (int)(blockIdx.z + 1) * l.gl * 8); c0 += l.gl * 8) {
-    float2 rs[4], sh[4], mg[4], mgx[4];
+  for (int c0 = blockIdx.z * l.gl * 8 + l.tg * 8; l.tp < l.pl && c0 < min(C, (int)(blockIdx.z + 1) * l.gl * 8); c0 += l.gl * 8) {
+    float2 rs[4], sh[4], mg[4], mgx[4], vs[4];
     norm_consts(stats, n, C, c0, inv, rs, sh);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) vs[e] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const float* b0 = bst + ((size_t)n * C + c0 + 2 * e) * 2;
@@ -347,6 +364,7 @@ __global__ void __launch_bounds__(256, 3) k_in_bwd_apply_v8(const bf16* __restri
         if (act) g[e] = __fmul2_rn(g[e], act_bwd_fast2(act, res ? __fadd2_rn(xh, bf2(rw[e])) : xh));
         const float2 t = __ffma2_rn(xh, mgx[e], __fadd2_rn(g[e], make_float2(-mg[e].x, -mg[e].y)));
         o[e] = __fmul2_rn(rs[e], t);
+        if (SUMS) vs[e] = __fadd2_rn(vs[e], o[e]);
       }
       uint4* dp = reinterpret_cast<uint4*>(dx + (base + p) * lddx + c0);
       if (acc_dx) {
@@ -365,6 +383,20 @@ __global__ void __launch_bounds__(256, 3) k_in_bwd_apply_v8(const bf16* __restri
           for (int e = 0; e < 4; ++e) g[e] = __fadd2_rn(g[e], bf2(owd[e]));
         }
         *rp = make_uint4(f2b(g[0]), f2b(g[1]), f2b(g[2]), f2b(g[3]));
+      }
+    }
+    if (SUMS) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { atomicAdd(&sacc[l.tg * 8 + 2 * e], vs[e].x); atomicAdd(&sacc[l.tg * 8 + 2 * e + 1], vs[e].y); }
+    }
+  }
+  if (SUMS) {
+    __syncthreads();
+    const int cb = blockIdx.z * l.gl * 8;
+    for (int i = threadIdx.x; i < l.gl * 8; i += 256) {
+      if (cb + i < C) {
+        if (dbias) atomicAdd(dbias + cb + i, sacc[i]);
+        if (dsum_nc) atomicAdd(dsum_nc + (size_t)n * C + cb + i, sacc[i]);
       }
     }
   }
@@ -454,20 +486,31 @@ int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const voi
 }
 int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const void* res, int ld_res, const void* dy,
                           int ld_dy, const float* bstats, void* dx, int ld_dx, int acc_dx, void* dres, int ld_dres,
-                          int acc_dres, int dtype, int N, long long HW, int C, int act, void* stream) {
+                          int acc_dres, int dtype, int N, long long HW, int C, int act, float* dbias, float* dsum_nc,
+                          void* stream) {
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy, dx, dres}, {ld_x, res ? ld_res : 0, ld_dy, ld_dx, dres ? ld_dres : 0})) {
     int ch;
-    static int slots = 0;
-    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8, &slots));
-    k_in_bwd_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
-                                                            (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
-                                                            (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch);
+    if (dbias || dsum_nc) {
+      static int slots = 0;
+      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<true>, &slots));
+      k_in_bwd_apply_v8<true><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
+                                                                    (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
+                                                                    (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch, dbias,
+                                                                    dsum_nc);
+    } else {
+      static int slots = 0;
+      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<false>, &slots));
+      k_in_bwd_apply_v8<false><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
+                                                                     (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
+                                                                     (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch, nullptr,
+                                                                     nullptr);
+    }
     return DS_LAUNCHED("inorm_bwd_apply_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
   DS_DISPATCH_DT(dtype, (k_in_bwd_apply<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
                             (const T*)x, ld_x, stats, (const T*)res, ld_res, (const T*)dy, ld_dy, bstats, (T*)dx, ld_dx,
-                            acc_dx, (T*)dres, ld_dres, acc_dres, HW, C, act)));
+                            acc_dx, (T*)dres, ld_dres, acc_dres, HW, C, act, dbias, dsum_nc)));
   return DS_LAUNCHED("inorm_bwd_apply");
 }
 }

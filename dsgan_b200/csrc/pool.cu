@@ -394,9 +394,46 @@ __global__ void k_ca_bwd(const float* __restrict__ ds, const float* __restrict__
     davg[(long long)n * C + c] = da; dmax[(long long)n * C + c] = dm;
   }
 }
+
+// Bias gradients of a MidMLKA (MixConvNeXtML.py:109-117) from per-plane fp32 statistics instead of a sum over the rounded
+// bf16 gradient tensor.  o = conv1x1(cat(dw_k(x))) + b_conv, then o * CA(o), then InstanceNorm:
+//   d b_conv[c]  = sum_n ( s[n,c] * S[n,c] + davg[n,c] + dmax[n,c] ),  S = sum_p of the norm's dx (fp32, ~0: dsgan_inorm_bwd_apply)
+//   d b_dw[c']   = sum_c W_conv[c,c'] * d b_conv[c]        (a depthwise bias shifts o by W_conv . b_dw)
+// one block; C <= 1024.
+__global__ void k_mid_bias_grads(const float* __restrict__ S, const float* __restrict__ s, const float* __restrict__ davg,
+                                 const float* __restrict__ dmax, int N, int C, const float* __restrict__ w,
+                                 float* __restrict__ d_conv_bias, float* __restrict__ dq0, float* __restrict__ dq1,
+                                 float* __restrict__ dq2, float* __restrict__ dq3) {
+  extern __shared__ float db[];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const long long o = (long long)n * C + c;
+      a += s[o] * S[o] + davg[o] + dmax[o];
+    }
+    db[c] = a;
+    atomicAdd(d_conv_bias + c, a);
+  }
+  __syncthreads();
+  const int q = C / 4;
+  for (int cp = threadIdx.x; cp < C; cp += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c) a = fmaf(w[(long long)c * C + cp], db[c], a);
+    float* dst = cp < q ? dq0 : (cp < 2 * q ? dq1 : (cp < 3 * q ? dq2 : dq3));
+    atomicAdd(dst + (cp % q), a);
+  }
+}
 }  // namespace
 
 extern "C" {
+int dsgan_mid_bias_grads(const float* dsum_nc, const float* s, const float* davg, const float* dmax, int N, int C,
+                         const float* w_conv, float* d_conv_bias, float* d_b3, float* d_b5, float* d_b7, float* d_b9,
+                         void* stream) {
+  DS_REQUIRE(C % 4 == 0 && C <= 4096, "mid_bias_grads: bad C=%d", C);
+  k_mid_bias_grads<<<1, 256, sizeof(float) * C, (cudaStream_t)stream>>>(dsum_nc, s, davg, dmax, N, C, w_conv, d_conv_bias,
+                                                                      d_b3, d_b5, d_b7, d_b9);
+  return DS_LAUNCHED("mid_bias_grads");
+}
 int dsgan_maxpool_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int N, int H, int W, int C, int k,
                       void* stream) {
   DS_REQUIRE(k >= 1 && H % k == 0 && W % k == 0, "maxpool: H,W (%d,%d) must be multiples of k=%d", H, W, k);

@@ -20,7 +20,7 @@ ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
 
 class Var:
     """An NHWC activation (or a channel slice of one) that can carry a gradient."""
-    __slots__ = ("t", "ptr", "N", "H", "W", "C", "ld", "es", "g", "parent", "coff", "fused_act")
+    __slots__ = ("t", "ptr", "N", "H", "W", "C", "ld", "es", "g", "parent", "coff", "fused_act", "bias_gptr", "bias_claimed")
 
     def __init__(self, t, N, H, W, C, ld=None, ptr=None, parent=None, coff=0):
         self.t, self.N, self.H, self.W, self.C = t, N, H, W, C
@@ -30,6 +30,9 @@ class Var:
         self.g = None          # dense gradient tensor [N,H,W,C] (same dtype as t)
         self.parent, self.coff = parent, coff
         self.fused_act = None  # (act, aux Var): this tensor is act(aux) and its grad is stored w.r.t. aux
+        # gradient address of the bias that produced this tensor when its ONLY consumer is an InstanceNorm: the norm's
+        # backward then delivers the bias gradient (fp32 sum of its dx, a structural zero) and the producer skips its colsum
+        self.bias_gptr, self.bias_claimed = None, False
 
     @property
     def npix(self):
@@ -488,7 +491,7 @@ def wst_convT_T(Ci, Co, k):       # ConvTranspose2d input-gradient / weight-grad
 # ------------------------------------------------------------------------------------------------
 
 def conv2d(ctx: Ctx, x: Var, w: Param, b, k, stride=1, pad=0, act=ACT_NONE, out: Var = None, acc=0,
-           need_dx=True, keep_pre=False):
+           need_dx=True, keep_pre=False, bias_via_in=False, bias_grad=True):
     """nn.Conv2d / nn.Linear (k=1) forward with fused bias + activation.  If `act` is set the returned Var is
     marked `fused_act`: consumers deliver its gradient already multiplied by act' (see conv dgrad / maxpool)."""
     Co, Ci = w.data.shape[0], w.data.shape[1]
@@ -512,6 +515,9 @@ def conv2d(ctx: Ctx, x: Var, w: Param, b, k, stride=1, pad=0, act=ACT_NONE, out:
     if act != ACT_NONE:
         y.fused_act = (act, pre if act == ACT_GELU else y)
     train_w = ctx.param_grads
+    if bias_via_in and b is not None and train_w and not ctx.no_grad:
+        assert act == ACT_NONE and not acc
+        y.bias_gptr = b.gptr
 
     def bwd():
         gi = y.grad_in()
@@ -522,8 +528,9 @@ def conv2d(ctx: Ctx, x: Var, w: Param, b, k, stride=1, pad=0, act=ACT_NONE, out:
                 ctx.tc_wgrad(gi, (x.ptr, x.ld), M, Co, Ci, w.gptr)
             else:
                 ctx.wgrad_raw(geom, (x.ptr, x.ld), gi, w.gptr, wst_conv(Co, Ci, k))
-            if b is not None:
+            if b is not None and y.bias_gptr is None and bias_grad:
                 ctx.colsum(gi, y.npix, Co, b.gptr)
+            assert y.bias_gptr is None or y.bias_claimed, "bias_via_in: no InstanceNorm consumed %s" % w.name
         if need_dx:
             conv2d_dgrad(ctx, x, gi, w, geom, pointwise)
     ctx.record(bwd)
@@ -546,7 +553,7 @@ def conv2d_dgrad(ctx, x: Var, gi, w: Param, geom, pointwise=False):
     ctx.conv_raw(g2, gi, w, wst_conv_T(Co, Ci, k), None, (gp, gld), dact=dact, acc=gacc, aux=aux, transposed=True)
 
 
-def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
+def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param, bias_via_in=False):
     """nn.ConvTranspose2d(k=3, s=2, p=1, output_padding=1) forward (MixConvNeXtML.py:53,150)."""
     Ci, Co, k = w.data.shape[0], w.data.shape[1], 3
     assert Ci == x.C
@@ -555,6 +562,8 @@ def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
     gf = (x.N, x.H, x.W, Ci, Ho, Wo, Co, k, 2, 1)
     ctx.conv_raw(gf, (x.ptr, x.ld), w, wst_convT(Ci, Co, k), b.ptr, (y.ptr, y.ld), transposed=True)
     train_w = ctx.param_grads
+    if bias_via_in and train_w and not ctx.no_grad:
+        y.bias_gptr = b.gptr
 
     def bwd():
         gi = y.grad_in()
@@ -564,7 +573,9 @@ def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param):
         gb = (x.N, Ho, Wo, Co, x.H, x.W, Ci, k, 2, 1)
         if train_w:
             ctx.wgrad_raw(gb, gi, (x.ptr, x.ld), w.gptr, wst_convT_T(Ci, Co, k))
-            ctx.colsum(gi, y.npix, Co, b.gptr)
+            if y.bias_gptr is None:
+                ctx.colsum(gi, y.npix, Co, b.gptr)
+            assert y.bias_gptr is None or y.bias_claimed, "bias_via_in: no InstanceNorm consumed %s" % w.name
         gp, gld, gacc = x.grad_out()
         assert x.fused_act is None
         ctx.conv_raw(gb, gi, w, wst_convT_T(Ci, Co, k), None, (gp, gld), acc=gacc)
@@ -577,13 +588,15 @@ def _label(ctx, x, extra=""):
         ctx.L.profiler.label = "C%d @%dx%d %s" % (x.C, x.H, x.W, extra)
 
 
-def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=True):
+def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=True, bias_via_in=False, bias_grad=True):
     """Depthwise k x k, stride 1, pad k//2 (MixConvNeXtML.py:94-97,220)."""
     y = out if out is not None else ctx.new(x.N, x.H, x.W, x.C)
     L, s = ctx.L, ctx.stream
     _label(ctx, x, "k%d" % k)
     L.dwconv_fwd(x.ptr, x.ld, w.ptr, b.ptr, y.ptr, y.ld, ctx.dt, x.N, x.H, x.W, x.C, k, 0, 0, s)
     train_w = ctx.param_grads
+    if bias_via_in and train_w and not ctx.no_grad:
+        y.bias_gptr = b.gptr
 
     def bwd():
         gi = y.grad_in()
@@ -591,7 +604,9 @@ def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=Tru
             return
         if train_w:
             _label(ctx, x, "k%d" % k)
-            L.dwconv_wgrad(x.ptr, x.ld, gi[0], gi[1], w.gptr, b.gptr, ctx.dt, x.N, x.H, x.W, x.C, k, ctx.stream)
+            assert y.bias_gptr is None or y.bias_claimed, "bias_via_in: no InstanceNorm consumed %s" % w.name
+            L.dwconv_wgrad(x.ptr, x.ld, gi[0], gi[1], w.gptr, b.gptr if (bias_grad and y.bias_gptr is None) else None,
+                           ctx.dt, x.N, x.H, x.W, x.C, k, ctx.stream)
         if not need_dx:
             return
         gp, gld, gacc = x.grad_out()
@@ -602,8 +617,13 @@ def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=Tru
     return y
 
 
-def inorm(ctx: Ctx, x: Var, act=ACT_NONE, res: Var = None, out: Var = None):
-    """y = act(InstanceNorm(x) + res); `out` may be a channel slice of a concat buffer."""
+def inorm(ctx: Ctx, x: Var, act=ACT_NONE, res: Var = None, out: Var = None, dsum_nc=None):
+    """y = act(InstanceNorm(x) + res); `out` may be a channel slice of a concat buffer.  If x carries `bias_gptr` (set by
+    its producer's bias_via_in) the backward pass adds the fp32 sum of dx into that bias gradient.  `dsum_nc`: optional
+    callable -> fp32 [N,C] tensor that receives the same sums per plane (MidMLKA bias gradients)."""
+    dbias = x.bias_gptr
+    if dbias is not None:
+        x.bias_claimed = True
     y = out if out is not None else ctx.new(x.N, x.H, x.W, x.C)
     L = ctx.L
     HW = x.H * x.W
@@ -628,8 +648,11 @@ def inorm(ctx: Ctx, x: Var, act=ACT_NONE, res: Var = None, out: Var = None):
             assert res.fused_act is None
         else:
             qp, qld, qacc = None, 0, 0
+        assert dbias is None or gacc == 0, "bias_via_in needs the norm to be the only consumer"
+        sums = dsum_nc() if dsum_nc is not None else None
         L.inorm_bwd_apply(x.ptr, x.ld, stats.data_ptr(), rp, rld, gi[0], gi[1], bst.data_ptr(), gp, gld, gacc,
-                          qp, qld, qacc, ctx.dt, x.N, HW, x.C, act, ctx.stream)
+                          qp, qld, qacc, ctx.dt, x.N, HW, x.C, act, dbias, sums.data_ptr() if sums is not None else None,
+                          ctx.stream)
     ctx.record(bwd)
     return y
 
@@ -687,8 +710,9 @@ def concat_into(ctx: Ctx, cat: Var, coff, src: Var):
     ctx.record(bwd)
 
 
-def ca_scale(ctx: Ctx, x: Var, fc1: Param, slope: Param, fc2: Param):
-    """y = x * CA(x)  (MixConvNeXtML.py:17-22,112)."""
+def ca_scale(ctx: Ctx, x: Var, fc1: Param, slope: Param, fc2: Param, mid_bias=None):
+    """y = x * CA(x)  (MixConvNeXtML.py:17-22,112).  `mid_bias` = (sums holder dict, conv weight, conv bias, [4 depthwise
+    biases]): the MidMLKA bias gradients are formed here from fp32 plane statistics (dsgan_mid_bias_grads)."""
     N, C, HW = x.N, x.C, x.H * x.W
     assert x.ld == x.C
     L = ctx.L
@@ -717,6 +741,10 @@ def ca_scale(ctx: Ctx, x: Var, fc1: Param, slope: Param, fc2: Param):
             d2 = dsl + 4
         L.ca_bwd(ds.data_ptr(), s.data_ptr(), avg.data_ptr(), mx.data_ptr(), N, C, fc1.ptr, slope.ptr, fc2.ptr,
                  d1, dsl, d2, davg.data_ptr(), dmax.data_ptr(), ctx.stream)
+        if mid_bias is not None and train_w:
+            holder, wc, bc, bq = mid_bias
+            L.mid_bias_grads(holder["S"].data_ptr(), s.data_ptr(), davg.data_ptr(), dmax.data_ptr(), N, C, wc.ptr,
+                             bc.gptr, bq[0].gptr, bq[1].gptr, bq[2].gptr, bq[3].gptr, ctx.stream)
         gp, gld, gacc = x.grad_out()
         assert gld == C and x.fused_act is None
         L.scale_nc_bwd_apply(gi[0], s.data_ptr(), davg.data_ptr(), dmax.data_ptr(), am.data_ptr(), gp, ctx.dt, N, HW,

@@ -24,6 +24,10 @@ class BaseModel:
             raise RuntimeError("dsgan_b200 runs on B200 GPUs only: gpu_ids=-1 (CPU) is the reference's path, "
                                "not this one (no CPU fallback)")
         self.device = torch.device("cuda:{}".format(self.gpu_ids[0]))
+        if len(self.gpu_ids) > 1:
+            import warnings
+            warnings.warn("gpu_ids=%s: only %s is used by this process; multi-GPU training is one process per GPU "
+                          "(torchrun), not nn.DataParallel (networks.py:77)" % (self.gpu_ids, self.device))
         self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
         self.loss_names, self.model_names, self.visual_names, self.image_paths = [], [], [], []
 
@@ -44,7 +48,7 @@ class BaseModel:
         pass  # no BatchNorm/Dropout on the built path: train and eval are numerically identical
 
     def test(self):
-        ctx = networks.get_ctx(self.device, self.precision)
+        ctx = self.netG.ctx()
         was, ctx.no_grad = ctx.no_grad, True
         try:
             self.forward()
@@ -71,12 +75,18 @@ class BaseModel:
 
     def save_networks(self, which_epoch):
         """<epoch>_useSE_net_<name>.pth holding net.state_dict() with DataParallel's `module.` prefix, exactly the
-        file the reference writes on GPU (base_model.py:92-103, Q16/Q17)."""
-        os.makedirs(self.save_dir, exist_ok=True)
-        for name in self.model_names:
-            net = getattr(self, "net" + name)
-            sd = OrderedDict(("module." + k, v.detach().cpu()) for k, v in net.state_dict().items())
-            torch.save(sd, os.path.join(self.save_dir, "%s_useSE_net_%s.pth" % (which_epoch, name)))
+        file the reference writes on GPU (base_model.py:92-103, Q16/Q17).  Under one-process-per-GPU data parallelism
+        only rank 0 writes (tmp file + atomic rename) and every rank waits for it."""
+        from .. import parallel
+        if parallel.rank() == 0:
+            os.makedirs(self.save_dir, exist_ok=True)
+            for name in self.model_names:
+                net = getattr(self, "net" + name)
+                sd = OrderedDict(("module." + k, v.detach().cpu()) for k, v in net.state_dict().items())
+                path = os.path.join(self.save_dir, "%s_useSE_net_%s.pth" % (which_epoch, name))
+                torch.save(sd, path + ".tmp")
+                os.replace(path + ".tmp", path)
+        parallel.barrier()
 
     def load_networks(self, which_epoch):
         """Reads <epoch>_net_<name>.pth like the reference (base_model.py:116-148) and, because the reference cannot

@@ -38,10 +38,17 @@ class Pix2PixModel(BaseModel):
         self.model_names = ["G", "D"] if self.isTrain else ["G"]
         self.use_gan, self.use_condition = opt.use_GAN, opt.use_condition
         self.w_vgg, self.w_tv, self.w_gan, self.w_ss = opt.w_vgg, opt.w_tv, opt.w_gan, opt.w_ss
+        # per-network activation precision (extension): --precision sets all three, --precision_{G,D,vgg} override one.
+        # The networks only meet at NCHW fp32 images (fake_B, dL/dfake_B), so each can run in its own engine context.
+        prec = {k: (getattr(opt, "precision_" + k, "") or self.precision) for k in ("G", "D", "vgg")}
+        self.precisions = prec
         networks.KernelNet.precision = self.precision
         self.netG = networks.define_G(opt.input_nc, opt.output_nc, opt.ngf, opt.which_model_netG, opt.norm,
                                       not opt.no_dropout, opt.init_type, self.gpu_ids)
-        self.ctx = networks.get_ctx(self.device, self.precision)
+        self.netG.precision = prec["G"]
+        self.ctx = self.ctxG = networks.get_ctx(self.device, prec["G"])
+        self.ctxD = networks.get_ctx(self.device, prec["D"])
+        self.ctxV = networks.get_ctx(self.device, prec["vgg"])
         self.world = parallel.world_size()
         self._in_buf, self._gs = {}, None
         self.use_graph = bool(int(getattr(opt, "cuda_graph", 1))) and self.isTrain
@@ -53,7 +60,16 @@ class Pix2PixModel(BaseModel):
             self.fake_AB_pool = ImagePool(opt.pool_size)
             self.use_lsgan = opt.no_lsgan  # the reference's inverted flag (pix2pix_model.py:98,112-114, Q6)
             self.criterionGAN = networks.GANLoss(use_lsgan=opt.no_lsgan).to(self.device)
+            self.netD.precision = prec["D"]
             self.vgg = Vgg16().to(self.device)
+            self.vgg.precision = prec["vgg"]
+            vw = getattr(opt, "vgg_weights", "")
+            if vw:
+                self.vgg.load_torchvision(vw)
+            elif float(self.w_vgg) != 0:
+                import warnings
+                warnings.warn("Vgg16 is RANDOM-initialised: pass --vgg_weights <torchvision vgg16 state_dict> to train with "
+                              "the reference's ImageNet perceptual loss (models/vgg.py:8 downloads it; no network here)")
             self.optimizer_G = FlatAdam(self.netG, lr=opt.lr, betas=(opt.beta1, 0.999))
             self.optimizer_D = FlatAdam(self.netD, lr=opt.lr, betas=(opt.beta1, 0.999))
             self.optimizers = [self.optimizer_G, self.optimizer_D]
@@ -86,31 +102,31 @@ class Pix2PixModel(BaseModel):
         self.image_paths = input["A_paths" if AtoB else "B_paths"]
 
     def forward(self):
-        self.ctx.clear()
+        self.ctxG.clear()
         self.fake_B = self.netG(self.real_A)
         self._g_out = self.netG.last_output
-        self._g_tape = self.ctx.take_tape()
+        self._g_tape = self.ctxG.take_tape()
 
     def _slot(self, name):
         return self._loss.data_ptr() + 4 * SLOT[name]
 
-    def _pair(self, a, b):
+    def _pair(self, ctx, a, b):
         """cat((a, b), 1) as one NHWC tensor (pix2pix_model.py:145,153,168)."""
         N, C, H, W = a.shape
-        v = self.ctx.new(N, H, W, C + b.shape[1])
-        image_to_nhwc(self.ctx, a, out=v.slice(0, C))
-        image_to_nhwc(self.ctx, b, out=v.slice(C, b.shape[1]))
+        v = ctx.new(N, H, W, C + b.shape[1])
+        image_to_nhwc(ctx, a, out=v.slice(0, C))
+        image_to_nhwc(ctx, b, out=v.slice(C, b.shape[1]))
         return v
 
     def _gan_kw(self):
         return dict(use_lsgan=self.use_lsgan, sigmoid_d=self.use_lsgan)
 
     def backward_D(self):
-        ctx = self.ctx
+        ctx = self.ctxD
         ctx.param_grads = True
         if self.use_condition == 1:
             xf = image_to_nhwc(ctx, self._pooled_fake().contiguous())
-            xr = self._pair(self.real_A, self.real_B)
+            xr = self._pair(ctx, self.real_A, self.real_B)
         else:
             xf, xr = image_to_nhwc(ctx, self.fake_B), image_to_nhwc(ctx, self.real_B)
         P = self.netD.params()  # (refreshes the bf16 operands once, before the two branches fork)
@@ -124,54 +140,54 @@ class Pix2PixModel(BaseModel):
         ctx.backward()  # loss_D = 0.5*(fake+real)
 
     def backward_G(self):
-        ctx = self.ctx
+        cG, cD, cV = self.ctxG, self.ctxD, self.ctxV
         fake, real = self.fake_B, self.real_B
         dfake = torch.empty_like(fake)
-        ctx.zero_(dfake)
-        ctx.param_grads = False  # D and VGG are frozen here (set_requires_grad(netD, False), vgg.py:27-28)
+        cG.zero_(dfake)
+        cD.param_grads = cV.param_grads = False  # D and VGG are frozen here (set_requires_grad(netD, False), vgg.py:27-28)
         # VGG(real_B) needs nothing from this step: run it (no tape) on the side stream, next to the discriminator's small
         # kernels; joined right before the feature losses.
         side = None
-        if ctx.use_streams and fake.is_cuda:
-            main = torch.cuda.current_stream(ctx.device)
-            if ctx._side_stream is None:
-                ctx._side_stream = torch.cuda.Stream(ctx.device)
-            side = ctx._side_stream
+        if cV.use_streams and fake.is_cuda:
+            main = torch.cuda.current_stream(cV.device)
+            if cV._side_stream is None:
+                cV._side_stream = torch.cuda.Stream(cV.device)
+            side = cV._side_stream
             Pv = self.vgg.params()   # on the MAIN stream: lazy flattening / operand refresh must be ordered before both passes
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                ctx.no_grad = True
-                fr = nets.vgg_forward(ctx, Pv, image_to_nhwc(ctx, real), need_dx=False)
-                ctx.no_grad = False
+                cV.no_grad = True
+                fr = nets.vgg_forward(cV, Pv, image_to_nhwc(cV, real), need_dx=False)
+                cV.no_grad = False
         if self.use_gan == 1:
-            x = self._pair(self.real_A, fake) if self.use_condition == 1 else image_to_nhwc(ctx, fake)
+            x = self._pair(cD, self.real_A, fake) if self.use_condition == 1 else image_to_nhwc(cD, fake)
             pred = self.netD.forward_var(x, need_dx=True)
-            losses.gan_loss(ctx, pred, True, self._slot("G_GAN"), 1.0, float(self.w_gan), **self._gan_kw())
-            ctx.backward()
+            losses.gan_loss(cD, pred, True, self._slot("G_GAN"), 1.0, float(self.w_gan), **self._gan_kw())
+            cD.backward()
             gv = x.slice(self.real_A.shape[1], fake.shape[1]) if self.use_condition == 1 else x
-            nhwc_grad_to_image(ctx, gv, dfake)
-        losses.l1_images(ctx, fake, real, self._slot("G_L1"), 1.0, dfake)
+            nhwc_grad_to_image(cD, gv, dfake)
+        losses.l1_images(cG, fake, real, self._slot("G_L1"), 1.0, dfake)
         # VGG perceptual loss on raw [-1,1] images (pix2pix_model.py:180-186, Q14)
         if side is None:
-            ctx.no_grad = True
-            fr = self.vgg.forward_var(image_to_nhwc(ctx, real), need_dx=False)
-            ctx.no_grad = False
-        xv = image_to_nhwc(ctx, fake)
+            cV.no_grad = True
+            fr = self.vgg.forward_var(image_to_nhwc(cV, real), need_dx=False)
+            cV.no_grad = False
+        xv = image_to_nhwc(cV, fake)
         ff = self.vgg.forward_var(xv, need_dx=True)
         if side is not None:
-            torch.cuda.current_stream(ctx.device).wait_stream(side)
+            torch.cuda.current_stream(cV.device).wait_stream(side)
         for f, r in zip(ff, fr):
-            losses.l1_features(ctx, f, r, self._slot("vgg"), float(self.w_vgg))
-        ctx.backward()
-        nhwc_grad_to_image(ctx, xv, dfake)
-        losses.tv_loss(ctx, fake, self._slot("tv"), float(self.w_tv) * parallel.tv_grad_scale(self.world), dfake)
-        losses.ssim_training_loss(ctx, real, fake, self._slot("ssim"), float(self.w_ss), dfake)
+            losses.l1_features(cV, f, r, self._slot("vgg"), float(self.w_vgg))
+        cV.backward()
+        nhwc_grad_to_image(cV, xv, dfake)
+        losses.tv_loss(cG, fake, self._slot("tv"), float(self.w_tv) * parallel.tv_grad_scale(self.world), dfake)
+        losses.ssim_training_loss(cG, real, fake, self._slot("ssim"), float(self.w_ss), dfake)
         # dL/dfake_B -> generator backward
-        ctx.param_grads = True
+        cD.param_grads = cV.param_grads = cG.param_grads = True
         gp, gld, _acc = self._g_out.grad_out()
-        ctx.L.nchw_to_nhwc(dfake.data_ptr(), gp, ctx.dt, fake.shape[0], fake.shape[1], fake.shape[2], fake.shape[3],
-                           gld, 1.0, 0.0, ctx.stream)
-        ctx.backward(self._g_tape)
+        cG.L.nchw_to_nhwc(dfake.data_ptr(), gp, cG.dt, fake.shape[0], fake.shape[1], fake.shape[2], fake.shape[3],
+                          gld, 1.0, 0.0, cG.stream)
+        cG.backward(self._g_tape)
         self._g_tape = self._g_out = None
 
     def _allreduce(self, net):
@@ -269,10 +285,14 @@ class Pix2PixModel(BaseModel):
                     fn()
             plan.append(("graph", g))
         gs["plan"], gs["ptrs"] = plan, self._flat_ptrs()
+        gs["fake_B"] = self.fake_B      # the tensor the captured forward writes (lives in the graphs' memory pool)
         gs["kernels_per_replay"] = int(self.ctx.L.cdll.dsgan_launch_count() - n0)   # launches recorded into the graphs
         torch.cuda.synchronize()
 
     def _replay(self, gs):
+        # forward()/test() outside the graphs (get_img_gen after every step in the reference's train.py:112) re-bind
+        # self.fake_B to a fresh eager tensor; the eager image-pool segment and the visuals must see the captured one.
+        self.fake_B = gs["fake_B"]
         if self.use_gan == 1:
             self.optimizer_D.advance()
         self.optimizer_G.advance()
@@ -287,7 +307,7 @@ class Pix2PixModel(BaseModel):
         if not (self.use_graph and self.ctx.profile is None):
             return self._eager_step()
         key = (tuple(self.real_A.shape), tuple(self.real_B.shape), self.real_A.data_ptr(), self.real_B.data_ptr(),
-               self.world, self.ctx.use_streams)
+               self.world, self.ctxG.use_streams, self.ctxD.use_streams, self.ctxV.use_streams)
         gs = self._gs
         if gs is None or gs["key"] != key or (gs.get("plan") is not None and gs["ptrs"] != self._flat_ptrs()):
             self._gs = gs = {"key": key, "warm": 0, "plan": None, "pool_in": None}

@@ -116,7 +116,7 @@ def _block(ctx: Ctx, P, p, x: Var, out: Var = None, need_dx=True):
     # the shortcut writes y first and pwconv2 accumulates into it, so that in the backward pass (reverse order) the depthwise
     # input-gradient OVERWRITES dL/dx and the shortcut's GEMM epilogue does the fan-in add (cheaper than a depthwise RMW)
     y = conv2d(ctx, x, P[p + ".shortcut.weight"], None, 1, out=out, need_dx=need_dx)
-    t = dwconv(ctx, x, P[p + ".dwconv.weight"], P[p + ".dwconv.bias"], 7, need_dx=need_dx)
+    t = dwconv(ctx, x, P[p + ".dwconv.weight"], P[p + ".dwconv.bias"], 7, need_dx=need_dx, bias_via_in=True)
     t = inorm(ctx, t)
     h = conv2d(ctx, t, P[p + ".pwconv1.weight"], P[p + ".pwconv1.bias"], 1, act=ACT_GELU)
     conv2d(ctx, h, P[p + ".pwconv2.weight"], P[p + ".pwconv2.bias"], 1, out=y, acc=1)
@@ -125,7 +125,7 @@ def _block(ctx: Ctx, P, p, x: Var, out: Var = None, need_dx=True):
 
 def _upsample(ctx: Ctx, P, p, x: Var, skip: Var):
     """upSample (MixConvNeXtML.py:60-66): ConvT -> IN -> GELU written straight into the concat buffer."""
-    t = conv_transpose2d(ctx, x, P[p + ".weight"], P[p + ".bias"])
+    t = conv_transpose2d(ctx, x, P[p + ".weight"], P[p + ".bias"], bias_via_in=True)
     par = skip.parent
     if par is not None and par.parent is None and skip.coff == t.C and par.C == t.C + skip.C:
         cat = par        # the skip tensor was produced in place in channels [C, 2C) of this concat buffer: nothing to copy
@@ -148,12 +148,21 @@ def _midmlka(ctx: Ctx, P, p, x: Var):
     """MidMLKA (MixConvNeXtML.py:109-117)."""
     q = x.C // 4
     cat = ctx.new(x.N, x.H, x.W, x.C)
+    # The five biases of this module sit in front of an InstanceNorm (through the CA gate): their gradients are near-zero
+    # sums that must not be taken over rounded bf16 tensors -> formed from fp32 plane statistics in ca_scale's backward.
     for i, k in enumerate((3, 5, 7, 9)):
         dwconv(ctx, x.slice(i * q, q), P["%s.X%d.weight" % (p, k)], P["%s.X%d.bias" % (p, k)], k,
-               out=cat.slice(i * q, q))
-    o = conv2d(ctx, cat, P[p + ".conv.weight"], P[p + ".conv.bias"], 1)
-    o = ca_scale(ctx, o, P[p + ".attn.fc1.weight"], P[p + ".attn.relu1.weight"], P[p + ".attn.fc2.weight"])
-    return inorm(ctx, o, act=ACT_GELU, res=x)  # IN, then += x, then GELU (Q3)
+               out=cat.slice(i * q, q), bias_grad=False)
+    o = conv2d(ctx, cat, P[p + ".conv.weight"], P[p + ".conv.bias"], 1, bias_grad=False)
+    holder = {}
+
+    def sums():
+        holder["S"] = ctx.zeros_f32(x.N, x.C)
+        return holder["S"]
+    o = ca_scale(ctx, o, P[p + ".attn.fc1.weight"], P[p + ".attn.relu1.weight"], P[p + ".attn.fc2.weight"],
+                 mid_bias=(holder, P[p + ".conv.weight"], P[p + ".conv.bias"],
+                           [P["%s.X%d.bias" % (p, k)] for k in (3, 5, 7, 9)]))
+    return inorm(ctx, o, act=ACT_GELU, res=x, dsum_nc=sums)  # IN, then += x, then GELU (Q3)
 
 
 def _local(ctx: Ctx, P, x: Var):
@@ -171,7 +180,7 @@ def _local(ctx: Ctx, P, x: Var):
                                                P[L + "upc1.0.weight"], None, 1))
     u2 = _midmlka(ctx, P, L + "upc2", _upsample(ctx, P, L + "up2.model.0", u1, d4))
     u3 = _midmlka(ctx, P, L + "upc3", _upsample(ctx, P, L + "up3.model.0", u2, d3))
-    u4 = inorm(ctx, conv_transpose2d(ctx, u3, P[L + "up4.0.weight"], P[L + "up4.0.bias"]))
+    u4 = inorm(ctx, conv_transpose2d(ctx, u3, P[L + "up4.0.weight"], P[L + "up4.0.bias"], bias_via_in=True))
     sc = conv2d(ctx, x, P[L + "shortcut.0.weight"], None, 1, need_dx=False)
     return inorm(ctx, sc, act=ACT_GELU, res=u4)  # GELU(IN(up4) + IN(shortcut))
 
@@ -217,15 +226,18 @@ def discriminator_forward(ctx: Ctx, P, x: Var, need_dx=True) -> Var:
     """NLayerDiscriminator (networks.py:543-579): logits N x 30 x 30 x 1 (NHWC)."""
     h = conv2d(ctx, x, P["model.0.weight"], P["model.0.bias"], 4, 2, 1, act=ACT_LEAKY, need_dx=need_dx)
     for m, st in specs.D_LAYERS[1:4]:
-        h = conv2d(ctx, h, P["model.%d.weight" % m], P["model.%d.bias" % m], 4, st, 1)
+        h = conv2d(ctx, h, P["model.%d.weight" % m], P["model.%d.bias" % m], 4, st, 1, bias_via_in=True)
         h = inorm(ctx, h, act=ACT_LEAKY)
     return conv2d(ctx, h, P["model.11.weight"], P["model.11.bias"], 4, 1, 1)
 
 
-def vgg_forward(ctx: Ctx, P, x: Var, need_dx=True):
-    """Vgg16 taps relu1_2, relu2_2, relu3_3, relu4_3 (vgg.py:30-38); weights are frozen (vgg.py:27-28)."""
+def vgg_forward(ctx: Ctx, P, x: Var, need_dx=True, with_tail=False):
+    """Vgg16 taps relu1_2, relu2_2, relu3_3, relu4_3 (vgg.py:30-38); weights are frozen (vgg.py:27-28).  `with_tail`
+    also runs the relu5_3 block (vgg.py:39-41): the training loss never reads it (pix2pix_model.py:182-186), the public
+    Vgg16.forward returns it like the reference."""
     taps, h, first = [], x, True
-    for e in specs.VGG_PLAN:
+    plan = specs.VGG_PLAN + (("P",) + specs.VGG_TAIL + ("T",) if with_tail else ())
+    for e in plan:
         if e == "T":
             taps.append(h)
         elif e == "P":

@@ -42,6 +42,13 @@ BASE_FLAGS = [
     ("--w_tv", dict(default=1)), ("--w_ss", dict(default=1.25)), ("--use_condition", dict(default=1)),
     # extension (not in the reference): activation precision of the sm_100a kernels
     ("--precision", dict(type=str, default="bf16", choices=["bf16", "fp32"])),
+    # extension: per-network override of --precision (the networks only meet at NCHW fp32 images)
+    ("--precision_G", dict(type=str, default="", choices=["", "bf16", "fp32"])),
+    ("--precision_D", dict(type=str, default="", choices=["", "bf16", "fp32"])),
+    ("--precision_vgg", dict(type=str, default="", choices=["", "bf16", "fp32"])),
+    # extension: ImageNet VGG16 weights for the perceptual loss (torchvision vgg16 state_dict).  The reference downloads them
+    # (vgg.py:8); without a file the VGG is random-initialised and a warning is printed.
+    ("--vgg_weights", dict(type=str, default="")),
     # extension: replay optimize_parameters() as CUDA graphs after two eager warm-up steps (0 = always eager)
     ("--cuda_graph", dict(type=int, default=1)),
 ]

@@ -52,3 +52,8 @@ def broadcast_params(flat_params, src=0):
     if world_size() > 1:
         dist.broadcast(flat_params, src)
     return flat_params
+
+
+def barrier():
+    if world_size() > 1:
+        dist.barrier()

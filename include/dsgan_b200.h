@@ -186,10 +186,15 @@ int dsgan_inorm_apply(const void* x, int ld_x, const float* stats, const void* r
 /* bstats[n,c] = {sum g, sum g*xhat}, g = dy*act'(xhat+res)  (fp32 [N,C,2], overwritten). */
 int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const void* res, int ld_res, const void* dy,
                           int ld_dy, int dtype, int N, long long HW, int C, int act, float* bstats, void* stream);
-/* dx (=|+=) rstd*(g - mean(g) - xhat*mean(g*xhat));  dres (=|+=) g  (dres may be NULL). */
+/* dx (=|+=) rstd*(g - mean(g) - xhat*mean(g*xhat));  dres (=|+=) g  (dres may be NULL).
+ * dbias (fp32 [C], +=) / dsum_nc (fp32 [N,C], +=), both optional: the sum over pixels of THIS call's dx values in fp32,
+ * taken before the bf16 rounding and before any fan-in add.  It is the gradient of a bias feeding the norm (Conv2d /
+ * ConvTranspose2d / depthwise conv + InstanceNorm2d: MixConvNeXtML.py:53-54,220-221; networks.py:556-566): zero in exact
+ * arithmetic, fp32 round-off in the reference. */
 int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const void* res, int ld_res, const void* dy,
                           int ld_dy, const float* bstats, void* dx, int ld_dx, int acc_dx, void* dres, int ld_dres,
-                          int acc_dres, int dtype, int N, long long HW, int C, int act, void* stream);
+                          int acc_dres, int dtype, int N, long long HW, int C, int act, float* dbias, float* dsum_nc,
+                          void* stream);
 
 /* ---- pooling ------------------------------------------------------------------------------- */
 /* nn.MaxPool2d(k) (stride k), MixConvNeXtML.py:68-74,333-354; models/vgg.py pools. */
@@ -208,6 +213,11 @@ int dsgan_ca_fwd(const void* x, int dtype, int N, long long HW, int C, const flo
 int dsgan_ca_bwd(const float* ds, const float* s, const float* avg, const float* mx, int N, int C, const float* fc1,
                  const float* slope, const float* fc2, float* dfc1, float* dslope, float* dfc2, float* davg,
                  float* dmax, void* stream);
+/* Bias gradients of one MidMLKA from fp32 plane statistics (MixConvNeXtML.py:94-113): conv.bias[c] += sum_n(s*S + davg +
+ * dmax), X{3,5,7,9}.bias += W_conv^T . d conv.bias, with S = dsum_nc of dsgan_inorm_bwd_apply.  w_conv: fp32 [C,C]. */
+int dsgan_mid_bias_grads(const float* dsum_nc, const float* s, const float* davg, const float* dmax, int N, int C,
+                         const float* w_conv, float* d_conv_bias, float* d_b3, float* d_b5, float* d_b7, float* d_b9,
+                         void* stream);
 
 /* ---- losses --------------------------------------------------------------------------------- */
 /* GANLoss (networks.py:143-163): mode 0 = BCEWithLogits, 1 = MSE, 2 = MSE on sigmoid(pred) (the `--no_lsgan`

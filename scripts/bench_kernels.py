@@ -135,7 +135,7 @@ def main():
         emit(out, "inorm_stats 16x256x256x128 bf16", timeit(lambda: L.inorm_stats(x.ptr, 128, 1, 16, HW, 128, stats.data_ptr(), s)), bytes_=nb)
         emit(out, "inorm_apply+GELU", timeit(lambda: L.inorm_apply(x.ptr, 128, stats.data_ptr(), None, 0, y.ptr, 128, 1, 16, HW, 128, 3, s)), bytes_=2 * nb)
         emit(out, "inorm_bwd_stats (GELU)", timeit(lambda: L.inorm_bwd_stats(x.ptr, 128, stats.data_ptr(), None, 0, dy.ptr, 128, 1, 16, HW, 128, 3, bst.data_ptr(), s)), bytes_=2 * nb)
-        emit(out, "inorm_bwd_apply (GELU)", timeit(lambda: L.inorm_bwd_apply(x.ptr, 128, stats.data_ptr(), None, 0, dy.ptr, 128, bst.data_ptr(), dx.ptr, 128, 0, None, 0, 0, 1, 16, HW, 128, 3, s)), bytes_=3 * nb)
+        emit(out, "inorm_bwd_apply (GELU)", timeit(lambda: L.inorm_bwd_apply(x.ptr, 128, stats.data_ptr(), None, 0, dy.ptr, 128, bst.data_ptr(), dx.ptr, 128, 0, None, 0, 0, 1, 16, HW, 128, 3, None, None, s)), bytes_=3 * nb)
         # ---- depthwise 7x7 on the same tensor
         w = torch.randn(128, 1, 7, 7, device="cuda") * 0.1
         b = torch.zeros(128, device="cuda")
