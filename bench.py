@@ -89,36 +89,103 @@ def run_reference(args):
         O.train_step(PG, PD, PV, A, B, st)
     dt = time.perf_counter() - t0
     v = b * args.steps / dt
-    sample = "%d images/step x %d steps of the same 256x256 workload (per-GPU batch 16 on the GPU arm)" % (b, args.steps)
+    sample = "%d steps of %d images (256x256) of the same G+D training step, fp32, torch CPU" % (args.steps, b)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DS-GAN training step (MixConvNeXtML G + PatchGAN D + VGG/L1/TV/SSIM losses, 2x Adam), "
-                               "256x256, random-init weights; CPU oracle (port of the reference's torch-CPU path), "
-                               "bounded sample of %d images per step" % b,
-                   "images_per_step": b},
+                               "per-GPU batch %d, 256x256, random-init weights" % b,
+                   "per_gpu_batch": b, "global_batch": b, "parallelism": "cpu",
+                   "note": "CPU oracle (port of the reference's torch-CPU path, fp32) on rank 0's host cores; one step = the "
+                           "same %d-image batch the GPU arm runs per GPU" % b},
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def cpu_baseline(seconds=12.0):
+def cpu_baseline(batch=16, steps=2):
+    """The oracle (CPU port of the reference's own torch path) on the SAME per-step batch as the GPU arm, all host
+    threads, bounded to 1 warm-up + `steps` timed steps (~25 s on 16 cores)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dsgan_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     PG, PD, PV = O.init_params_G(20), O.init_params_D(20), O.init_params_vgg(20)
-    A, B = O.synthetic_pair(2, H, W, seed=1)
+    A, B = O.synthetic_pair(batch, H, W, seed=1)
     st = {}
     O.train_step(PG, PD, PV, A, B, st)
-    n, t0 = 0, time.perf_counter()
-    while n < 2 or time.perf_counter() - t0 < seconds:
+    t0 = time.perf_counter()
+    for _ in range(steps):
         O.train_step(PG, PD, PV, A, B, st)
-        n += 1
     dt = time.perf_counter() - t0
-    return {"value": 2 * n / dt, "unit": "img/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of 2 images (256x256) of the same G+D training step, fp32, torch CPU" % n}
+    return {"value": batch * steps / dt, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of %d images (256x256) of the same G+D training step, fp32, torch CPU" % (steps, batch)}
+
+
+def extra_configs(ctx, hbm, tf_burst):
+    """BASELINE configs[3] (MS-SSIM fwd+bwd sweep, 64x3x256x256, HBM GB/s) and configs[4] (generator-only inference,
+    32x512x512) measured in the same run: CUDA events, 3 warm-ups, median of 5, L2 flushed between iterations."""
+    import torch
+    from dsgan_b200 import losses
+    from dsgan_b200.models import networks
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def med(fn, iters=5, warm=3):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(1)
+    X = torch.rand(64, 3, 256, 256, device="cuda", generator=g)
+    Y = (X + 0.1 * torch.randn(X.shape, device="cuda", generator=g)).clamp(0, 1)
+    val, dY = torch.zeros(1, device="cuda"), torch.zeros_like(X)
+    ms = med(lambda: losses.ssim_value_and_grad(ctx, X, Y, val.data_ptr(), 1.0, dY, 1.0, multiscale=True))
+    nb = 5 * X.numel() * 4
+    out["ms_ssim_fwd_bwd_64x3x256x256"] = {"ms": ms, "algorithmic_bytes": nb, "achieved_gbs": nb / (ms * 1e-3) / 1e9,
+                                           "peak_gbs": hbm, "frac": nb / (ms * 1e-3) / 1e9 / hbm, "dtype": "f32"}
+    del X, Y, dY
+    was = networks.KernelNet.precision
+    networks.KernelNet.precision = "bf16"
+    G = networks.MixConvNeXtML().init_normal().cuda()
+    networks.KernelNet.precision = was
+    xin = torch.rand(32, 3, 512, 512, device="cuda", generator=g) * 2 - 1
+    gctx = G.ctx()
+
+    def infer():
+        gctx.no_grad = True
+        try:
+            G(xin)
+        finally:
+            gctx.no_grad = False
+            gctx.clear()
+    ms = med(infer, iters=3, warm=2)
+    fl = 2 * 40.77e9 * 4 * 32
+    out["generator_inference_32x3x512x512"] = {"ms": ms, "img_per_s": 32 / (ms * 1e-3), "algorithmic_flops": fl,
+                                               "achieved_tflops": fl / (ms * 1e-3) / 1e12, "peak_tflops": tf_burst,
+                                               "frac": fl / (ms * 1e-3) / 1e12 / tf_burst, "dtype": "bf16"}
+    return out
+
+
+def traffic_note():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r2_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum), beside its algorithmic bytes; None until a capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
 
 
 def run_ours(args):
@@ -136,6 +203,10 @@ def run_ours(args):
     from dsgan_b200.models import create_model
     from dsgan_b200.options.train_options import TrainOptions
 
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit("--global-batch %d is not divisible by %d GPUs" % (args.global_batch, world))
+        args.batch = args.global_batch // world
     opt = TrainOptions().parse("/tmp/none", "/tmp/dsgan_b200_bench",
                                argv=["--precision", args.precision, "--gpu_ids", str(local), "--batchSize", str(args.batch),
                                      "--cuda_graph", "0" if args.no_graph else "1"],
@@ -222,7 +293,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": imgs * args.steps / (ms * 1e-3), "unit": "img/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": {"workload": "DS-GAN training step (MixConvNeXtML G + PatchGAN D + VGG/L1/TV/SSIM losses, 2x Adam), "
                                "per-GPU batch %d, 256x256, random-init weights" % b,
                    "per_gpu_batch": b, "global_batch": imgs, "parallelism": "dp%d" % world,
@@ -235,12 +306,18 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": dense["name"], "achieved": achieved, "peak": tf_sust,
                      "unit": "TFLOP/s", "frac": achieved / tf_sust, "peak_source": which + " (sustained bf16)",
-                     "traffic": None, "launches_per_step": dense["n"], "ms_per_step": dense["ms"],
+                     "traffic": traffic_note(), "launches_per_step": dense["n"], "ms_per_step": dense["ms"],
                      "share_of_step": dense["ms"] / (ms / args.steps),
                      "families": {k: {"ms": v["ms"], "n": v["n"]} for k, v in prof.items()}},
     }
+    out["parity"] = {"mode": "bf16 activations / fp32 accumulate, statistics, losses and master weights",
+                     "meets": "losses <= 1e-3, fake_B <= 3e-2, G gradients <= 3e-2 (whole-net, configs[1])",
+                     "open": "D gradients 6-8e-2 end to end: fake_B's bf16 error x the ~3-20x conditioning of the "
+                             "real/fake cancellation in D's loss (profiles/r2_error_budget.json)"}
+    if world == 1 and not args.no_extra:
+        out["extra_configs"] = extra_configs(ctx, hbm, tf_burst)
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline()
+        out["cpu_baseline"] = cpu_baseline(b if b <= 16 else 16)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -275,7 +352,11 @@ def _main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE configs[1] = 16)")
-    ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=2, help="images per CPU reference step")
+    ap.add_argument("--cpu-batch", dest="cpu_batch", type=int, default=16,
+                    help="images per CPU reference step (default: the GPU arm's per-GPU batch)")
+    ap.add_argument("--global-batch", dest="global_batch", type=int, default=0,
+                    help="strong scaling: fixed global batch split over the GPUs (BASELINE configs[2]: 128)")
+    ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the configs[3]/[4] side measurements")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
     ap.add_argument("--detail", action="store_true", help="print the per-kernel profile to stderr")

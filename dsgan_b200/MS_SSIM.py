@@ -68,7 +68,7 @@ class _SSIMFn(torch.autograd.Function):
             for lv in range(5):
                 m = sums[lv, :, 0 if lv == 4 else 1] / float((h - 10) * (w - 10))
                 per = per * torch.relu(m) ** MS_WEIGHTS[lv]
-                h, w = h // 2, w // 2
+                h, w = h // 2 + h % 2, w // 2 + w % 2
         fctx.dY = None  # per-image gradients are not provided
         return per.view(N, C).mean(1)
 

@@ -278,29 +278,42 @@ __global__ void __launch_bounds__(256) k_ssim_bwd(const float* __restrict__ X, c
   }
 }
 
+// F.avg_pool2d(x, kernel_size=2, padding=(H % 2, W % 2)) (MS_SSIM.py:214-216; count_include_pad=True): an odd side is
+// zero-padded by one row / column on BOTH sides, output floor(H/2) + 1, window i covers rows 2i - ph, 2i - ph + 1; the
+// divisor stays 4.  Even sizes: ph = pw = 0, the plain 2x2 mean.
 __global__ void k_avgpool2_fwd(const float* __restrict__ x, float* __restrict__ y, int H, int W, long long total) {
-  const int Ho = H / 2, Wo = W / 2;
+  const int ph = H & 1, pw = W & 1, Ho = H / 2 + ph, Wo = W / 2 + pw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(i % Wo);
     const long long r = i / Wo;
     const int oy = (int)(r % Ho);
     const long long nc = r / Ho;
-    const float* p = x + (nc * H + 2 * oy) * W + 2 * ox;
-    y[i] = 0.25f * (p[0] + p[1] + p[W] + p[W + 1]);
+    const int y0 = 2 * oy - ph, x0 = 2 * ox - pw;
+    const float* p = x + nc * H * W;
+    float a = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = y0 + dy, xx = x0 + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) a += p[(long long)yy * W + xx];
+      }
+    y[i] = 0.25f * a;
   }
 }
 __global__ void k_avgpool2_bwd(const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int accum,
                                long long total) {
-  const int Ho = H / 2, Wo = W / 2;
+  const int ph = H & 1, pw = W & 1, Ho = H / 2 + ph, Wo = W / 2 + pw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int xx = (int)(i % W);
     const long long r = i / W;
     const int yy = (int)(r % H);
     const long long nc = r / H;
+    const int oy = (yy + ph) / 2, ox = (xx + pw) / 2;     // the one window that contains input pixel (yy, xx)
     float g = 0.f;
-    if (yy / 2 < Ho && xx / 2 < Wo) g = 0.25f * dy[(nc * Ho + yy / 2) * Wo + xx / 2];
+    if (oy < Ho && ox < Wo) g = 0.25f * dy[(nc * Ho + oy) * Wo + ox];
     dx[i] = accum ? dx[i] + g : g;
   }
 }
@@ -404,13 +417,11 @@ int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C
   return DS_LAUNCHED("ssim_bwd");
 }
 int dsgan_avgpool2_fwd(const float* x, float* y, int NC, int H, int W, void* stream) {
-  DS_REQUIRE(H % 2 == 0 && W % 2 == 0, "avgpool2: odd size %dx%d", H, W);
-  const long long total = (long long)NC * (H / 2) * (W / 2);
+  const long long total = (long long)NC * (H / 2 + (H & 1)) * (W / 2 + (W & 1));
   k_avgpool2_fwd<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, H, W, total);
   return DS_LAUNCHED("avgpool2_fwd");
 }
 int dsgan_avgpool2_bwd(const float* dy, float* dx, int NC, int H, int W, int accumulate, void* stream) {
-  DS_REQUIRE(H % 2 == 0 && W % 2 == 0, "avgpool2: odd size %dx%d", H, W);
   const long long total = (long long)NC * H * W;
   k_avgpool2_bwd<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, dx, H, W, accumulate, total);
   return DS_LAUNCHED("avgpool2_bwd");

@@ -58,6 +58,41 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   }
   return 0;
 }
+// ---- host side --------------------------------------------------------------------------------------------------
+struct MapKey {
+  const void* base; uint64_t d0, d1, s0; uint32_t b0, b1;
+  bool operator<(const MapKey& o) const {
+    return std::tie(base, d0, d1, s0, b0, b1) < std::tie(o.base, o.d0, o.d1, o.s0, o.b0, o.b1);
+  }
+};
+std::map<MapKey, CUtensorMap> g_maps;
+std::mutex g_maps_mu;
+
+// 2-D bf16 tensor map: dims {inner, outer}, row pitch in elements, box {b0, b1}
+int get_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t b0,
+               uint32_t b1) {
+  MapKey k{base, inner, outer, pitch_elems * 2, b0, b1};
+  std::lock_guard<std::mutex> lk(g_maps_mu);
+  auto it = g_maps.find(k);
+  if (it != g_maps.end()) { *out = it->second; return 0; }
+  uint64_t dims[2] = {inner, outer}, strides[1] = {pitch_elems * 2};
+  uint32_t box[2] = {b0, b1};
+  if (encode_tmap_bf16(out, base, 2, dims, strides, box, nullptr)) return 1;
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps[k] = *out;
+  return 0;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
 }  // namespace tc
 }  // namespace dsgan
 
@@ -318,41 +353,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
-}
-
-// ---- host side --------------------------------------------------------------------------------------------------
-struct MapKey {
-  const void* base; uint64_t d0, d1, s0; uint32_t b0, b1;
-  bool operator<(const MapKey& o) const {
-    return std::tie(base, d0, d1, s0, b0, b1) < std::tie(o.base, o.d0, o.d1, o.s0, o.b0, o.b1);
-  }
-};
-std::map<MapKey, CUtensorMap> g_maps;
-std::mutex g_maps_mu;
-
-// 2-D bf16 tensor map: dims {inner, outer}, row pitch in elements, box {b0, b1}
-int get_map_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t b0,
-               uint32_t b1) {
-  MapKey k{base, inner, outer, pitch_elems * 2, b0, b1};
-  std::lock_guard<std::mutex> lk(g_maps_mu);
-  auto it = g_maps.find(k);
-  if (it != g_maps.end()) { *out = it->second; return 0; }
-  uint64_t dims[2] = {inner, outer}, strides[1] = {pitch_elems * 2};
-  uint32_t box[2] = {b0, b1};
-  if (encode_tmap_bf16(out, base, 2, dims, strides, box, nullptr)) return 1;
-  if (g_maps.size() > 4096) g_maps.clear();
-  g_maps[k] = *out;
-  return 0;
-}
-
-int g_num_sms = 0;
-int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return g_num_sms;
 }
 
 template <int BN, int MODE>

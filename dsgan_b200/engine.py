@@ -87,7 +87,7 @@ class Param:
         return self.grad.data_ptr()
 
 
-FAMILY = {"conv_fwd": "dense", "conv_wgrad": "dense", "tc_gemm": "dense", "tc_wgrad": "dense", "tc_conv": "dense",
+FAMILY = {"fused_mlp_fwd": "dense", "fused_mlp_bwd": "dense", "mid_bias_grads": "ca", "conv_fwd": "dense", "conv_wgrad": "dense", "tc_gemm": "dense", "tc_wgrad": "dense", "tc_conv": "dense",
           "tc_conv_wgrad": "dense", "pack_conv_weight": "optim", "pack_conv_weights": "optim",
           "colsum": "reduce", "dwconv_fwd": "dwconv", "dwconv_wgrad": "dwconv",
           "inorm_stats": "norm", "inorm_apply": "norm", "inorm_bwd_stats": "norm", "inorm_bwd_apply": "norm",
@@ -551,6 +551,68 @@ def conv2d_dgrad(ctx, x: Var, gi, w: Param, geom, pointwise=False):
         return
     g2 = (N, Ho, Wo, Co, Hi, Wi, Ci, k, s, p)
     ctx.conv_raw(g2, gi, w, wst_conv_T(Co, Ci, k), None, (gp, gld), dact=dact, acc=gacc, aux=aux, transposed=True)
+
+
+def fused_mlp_ok(ctx: Ctx, x: Var, t: Var, y: Var, params):
+    """The fused Block-MLP kernels (csrc/fused_mlp.cu) apply in bf16 mode to C_in in {64,128,256}, N_out in {64,128,256}."""
+    if ctx.dt != BF16 or not ctx.use_tc or not getattr(ctx, "use_fused_mlp", True):
+        return False
+    Cin, Nout = x.C, y.C
+    if not ctx.L.cdll.dsgan_fused_mlp_supported(Cin, Nout):
+        return False
+    if any(p.bf16_ptr == 0 or p.bf16_ptr % 16 for p in params):
+        return False
+    return not (x.ld % 8 or t.ld % 8 or y.ld % 16 or x.ptr % 16 or t.ptr % 16 or y.ptr % 32)
+
+
+def block_mlp(ctx: Ctx, x: Var, t_fn, w1: Param, b1: Param, w2: Param, b2: Param, ws: Param, out: Var = None,
+              need_dx=True):
+    """y = shortcut(x) + pwconv2(GELU(pwconv1(t))) with t = t_fn() (the depthwise + norm branch of a ConvNeXt Block,
+    MixConvNeXtML.py:230-243) through the fused tcgen05 kernels: the 4C hidden stays on chip in the forward pass and is
+    recomputed in the backward pass.  Tape order: the shortcut's backward is recorded BEFORE t_fn's ops, so that in the
+    reverse pass the depthwise input-gradient overwrites dL/dx and the shortcut's GEMM epilogue does the fan-in add."""
+    Cin, Nout, H4 = x.C, ws.data.shape[0], w1.data.shape[0]
+    M = x.npix
+    y = out if out is not None else ctx.new(x.N, x.H, x.W, Nout)
+    train_w = ctx.param_grads
+    geom = (x.N, x.H, x.W, Cin, x.H, x.W, Nout, 1, 1, 0)
+
+    def bwd_shortcut():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        if train_w:
+            ctx.tc_wgrad(gi, (x.ptr, x.ld), M, Nout, Cin, ws.gptr)
+        if need_dx:
+            conv2d_dgrad(ctx, x, gi, ws, geom, True)
+    ctx.record(bwd_shortcut)
+    t = t_fn()
+    L = ctx.L
+    if L.profiler is not None:
+        L.profiler.pending_flops = 2.0 * M * (Cin * H4 + H4 * Nout + Cin * Nout)
+        L.profiler.label = "M%d %d->%d->%d" % (M, Cin, H4, Nout)
+    L.fused_mlp_fwd(t.ptr, t.ld, x.ptr, x.ld, M, Cin, Nout, w1.bf16_ptr, b1.ptr, w2.bf16_ptr, b2.ptr, ws.bf16_ptr, y.ptr,
+                    y.ld, ctx.stream)
+
+    def bwd_mlp():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        G = torch.empty((M, H4), dtype=torch.bfloat16, device=ctx.device)
+        A = torch.empty((M, H4), dtype=torch.bfloat16, device=ctx.device)
+        gp, gld, gacc = t.grad_out()
+        assert gacc == 0 and t.fused_act is None
+        if L.profiler is not None:   # algorithmic: the two input-gradient GEMMs (the recomputed pwconv1 earns no credit)
+            L.profiler.pending_flops = 2.0 * M * (H4 * Nout + H4 * Cin)
+            L.profiler.label = "M%d %d->%d->%d" % (M, Cin, H4, Nout)
+        L.fused_mlp_bwd(t.ptr, t.ld, gi[0], gi[1], M, Cin, Nout, w1.bf16_ptr, b1.ptr, w2.bf16_ptr, gp, gld, G.data_ptr(),
+                        A.data_ptr(), b1.gptr if train_w else None, ctx.stream)
+        if train_w:
+            ctx.tc_wgrad((G.data_ptr(), H4), (t.ptr, t.ld), M, H4, Cin, w1.gptr)
+            ctx.tc_wgrad(gi, (A.data_ptr(), H4), M, Nout, H4, w2.gptr)
+            ctx.colsum(gi, M, Nout, b2.gptr)
+    ctx.record(bwd_mlp)
+    return y
 
 
 def conv_transpose2d(ctx: Ctx, x: Var, w: Param, b: Param, bias_via_in=False):

@@ -34,7 +34,7 @@ def _workspace(X, levels, want):
         ws = {"sums": f(levels, N * C, 2), "coef": f(levels, N * C, 2) if want else None, "px": [], "py": [], "g": []}
         h, w = H, W
         for lv in range(1, levels):
-            h, w = h // 2, w // 2
+            h, w = h // 2 + h % 2, w // 2 + w % 2   # avg_pool2d(kernel 2, padding = side % 2), MS_SSIM.py:214-216
             ws["px"].append(f(N, C, h, w))
             ws["py"].append(f(N, C, h, w))
             ws["g"].append(f(N, C, h, w) if want else None)
@@ -112,8 +112,6 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
         L_.ssim_fwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, sums[lv].data_ptr(), ctx.stream)
         sizes.append((h - 10) * (w - 10))
         if lv < levels - 1:
-            if h % 2 or w % 2:
-                raise ValueError("ms_ssim: odd pyramid level %dx%d is not supported" % (h, w))
             nx, ny = ws["px"][lv], ws["py"][lv]
             L_.avgpool2_fwd(xs[lv].data_ptr(), nx.data_ptr(), NC, h, w, ctx.stream)
             L_.avgpool2_fwd(ys[lv].data_ptr(), ny.data_ptr(), NC, h, w, ctx.stream)

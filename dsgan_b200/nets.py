@@ -13,8 +13,8 @@ import torch
 import torch.nn as nn
 
 from . import specs
-from .engine import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, Ctx, Param, Var, add_n, ca_scale, concat_into, conv2d,
-                     conv_transpose2d, dwconv, image_to_nhwc, inorm, maxpool)
+from .engine import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, Ctx, Param, Var, add_n, block_mlp, ca_scale, concat_into,
+                     conv2d, conv_transpose2d, dwconv, fused_mlp_ok, image_to_nhwc, inorm, maxpool)
 
 
 class ParamTree(nn.Module):
@@ -113,13 +113,25 @@ class ParamTree(nn.Module):
 
 def _block(ctx: Ctx, P, p, x: Var, out: Var = None, need_dx=True):
     """ConvNeXt Block (MixConvNeXtML.py:230-243): dw7x7 -> IN -> Linear(C,4C) -> GELU -> Linear(4C,P) (+) 1x1 shortcut."""
+    W1, b1, W2, b2, Ws = (P[p + s] for s in (".pwconv1.weight", ".pwconv1.bias", ".pwconv2.weight", ".pwconv2.bias",
+                                             ".shortcut.weight"))
+
+    def branch():
+        t = dwconv(ctx, x, P[p + ".dwconv.weight"], P[p + ".dwconv.bias"], 7, need_dx=need_dx, bias_via_in=True)
+        return inorm(ctx, t)
+    y_probe = out if out is not None else None
+    plans = Ws.data.shape[0]
+    if y_probe is None:
+        y_probe = ctx.new(x.N, x.H, x.W, plans)
+    if fused_mlp_ok(ctx, x, x, y_probe, (W1, W2, Ws)):
+        # fused tcgen05 MLP: the 4C hidden never reaches HBM in the forward pass, is recomputed in the backward pass
+        return block_mlp(ctx, x, branch, W1, b1, W2, b2, Ws, out=y_probe, need_dx=need_dx)
     # the shortcut writes y first and pwconv2 accumulates into it, so that in the backward pass (reverse order) the depthwise
     # input-gradient OVERWRITES dL/dx and the shortcut's GEMM epilogue does the fan-in add (cheaper than a depthwise RMW)
-    y = conv2d(ctx, x, P[p + ".shortcut.weight"], None, 1, out=out, need_dx=need_dx)
-    t = dwconv(ctx, x, P[p + ".dwconv.weight"], P[p + ".dwconv.bias"], 7, need_dx=need_dx, bias_via_in=True)
-    t = inorm(ctx, t)
-    h = conv2d(ctx, t, P[p + ".pwconv1.weight"], P[p + ".pwconv1.bias"], 1, act=ACT_GELU)
-    conv2d(ctx, h, P[p + ".pwconv2.weight"], P[p + ".pwconv2.bias"], 1, out=y, acc=1)
+    y = conv2d(ctx, x, Ws, None, 1, out=y_probe, need_dx=need_dx)
+    t = branch()
+    h = conv2d(ctx, t, W1, b1, 1, act=ACT_GELU)
+    conv2d(ctx, h, W2, b2, 1, out=y, acc=1)
     return y
 
 

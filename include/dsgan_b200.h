@@ -106,6 +106,23 @@ int dsgan_tc_gemm(int mode, const void* A, int lda, const void* W, int ldb, long
 /* weight-gradient: dW[Co,Ci] (fp32, pitch ld_dw) += dY[P,Co]^T . X[P,Ci]; split over P, fp32 atomics. */
 int dsgan_tc_wgrad(const void* dY, int ld_dy, const void* X, int ld_x, long long P, int Co, int Ci, float* dW, int ld_dw,
                    void* stream);
+
+/* ---- fused ConvNeXt Block MLP (tcgen05, hidden kept on chip) ---------------------------------------------------
+ * Y[M,Nout] = X[M,Cin] . Ws[Nout,Cin]^T  +  GELU( T[M,Cin] . W1[4Cin,Cin]^T + b1 ) . W2[Nout,4Cin]^T + b2
+ * = Block.forward after the depthwise conv + norm (MixConvNeXtML.py:236-243: pwconv1 -> GELU -> pwconv2, + shortcut).
+ * T, X, Y: bf16 NHWC pixels with pitches ld_*; W1, W2, Ws: bf16 row-major (the networks' bf16 shadow); b1, b2: fp32.
+ * X / Ws may both be NULL (no shortcut), b2 may be NULL.  The 4Cin-wide hidden tensor never reaches HBM. */
+int dsgan_fused_mlp_supported(int Cin, int Nout);
+int dsgan_fused_mlp_fwd(const void* T, int ld_t, const void* X, int ld_x, long long M, int Cin, int Nout, const void* W1,
+                        const float* b1, const void* W2, const float* b2, const void* Ws, void* Y, int ld_y,
+                        void* stream);
+/* Backward of the MLP part (shortcut excluded) with the hidden recomputed:
+ *   Hpre = T.W1^T + b1;  A = GELU(Hpre);  G = (dY.W2) * GELU'(Hpre);  dT = G.W1      (MixConvNeXtML.py:236-240 backward)
+ * dT: bf16 [M,Cin] (overwritten).  G, A: bf16 [M,4Cin] workspaces, fully written - the operands of the two weight-gradient
+ * GEMMs (dW1 = G^T.T, dW2 = dY^T.A via dsgan_tc_wgrad).  db1 (fp32 [4Cin], +=, optional) = column sums of G. */
+int dsgan_fused_mlp_bwd(const void* T, int ld_t, const void* dY, int ld_dy, long long M, int Cin, int Nout, const void* W1,
+                        const float* b1, const void* W2, void* dT, int ld_dt, void* G, void* A, float* db1,
+                        void* stream);
 /* dst (bf16) = src (fp32), n elements: refresh of the packed GEMM operands after an optimizer step. */
 int dsgan_pack_bf16(const float* src, void* dst, long long n, void* stream);
 

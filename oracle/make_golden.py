@@ -116,12 +116,14 @@ def main():
     os.makedirs(out, exist_ok=True)
     p2p, ref_msssim = import_reference()
     torch.set_num_threads(os.cpu_count())
-    steps = [run_step(p2p, 2, 32, 0.05, 1), run_step(p2p, 1, 64, 0.0, 2), run_step(p2p, 1, 256, 0.05, 1),
-             run_step(p2p, 1, 256, 0.0, 1)]  # the last one is BASELINE config #1 with the reference's own init (bias 0)
-    with open(os.path.join(out, "train_step.json"), "w") as f:
-        json.dump(steps, f)
+    if "--skip-steps" not in sys.argv:
+        steps = [run_step(p2p, 2, 32, 0.05, 1), run_step(p2p, 1, 64, 0.0, 2), run_step(p2p, 1, 256, 0.05, 1),
+                 run_step(p2p, 1, 256, 0.0, 1)]  # the last one is BASELINE config #1 with the reference's own init (bias 0)
+        with open(os.path.join(out, "train_step.json"), "w") as f:
+            json.dump(steps, f)
     ms = [run_msssim(ref_msssim, 2, 256, 3, 0.1), run_msssim(ref_msssim, 2, 256, 4, None),
-          run_msssim(ref_msssim, 3, 48, 5, 0.2), run_msssim(ref_msssim, 1, 176, 6, 0.05)]
+          run_msssim(ref_msssim, 3, 48, 5, 0.2), run_msssim(ref_msssim, 1, 176, 6, 0.05),
+          run_msssim(ref_msssim, 1, 200, 7, 0.05)]   # 200 -> 100 -> 50 -> 25 -> 13: odd pyramid levels (padded avg_pool, :214-216)
     with open(os.path.join(out, "ms_ssim.json"), "w") as f:
         json.dump(ms, f)
     win = ref_msssim._fspecial_gauss_1d(11, 1.5).flatten().tolist()

@@ -73,7 +73,8 @@ def test_ssim_value_and_grad(shape, noise):
     assert torch.allclose(per, O.ssim(X, Y, 1.0, size_average=False), atol=2e-5)
 
 
-@pytest.mark.parametrize("shape,noise", [((2, 3, 256, 256), 0.1), ((2, 3, 256, 256), None), ((1, 3, 176, 192), 0.05)])
+@pytest.mark.parametrize("shape,noise", [((2, 3, 256, 256), 0.1), ((2, 3, 256, 256), None), ((1, 3, 176, 192), 0.05),
+                                         ((1, 3, 200, 168), 0.05), ((2, 2, 161, 250), 0.1)])   # odd pyramid levels
 def test_ms_ssim_value_and_grad(shape, noise):
     X = torch.rand(shape, generator=_g(3))
     Y = torch.rand(shape, generator=_g(4)) if noise is None else \
@@ -92,7 +93,8 @@ def test_ms_ssim_value_and_grad(shape, noise):
 
 def test_ms_ssim_against_reference_golden(golden_dir):
     """Fixtures written by the reference's own MS_SSIM.py (oracle/make_golden.py)."""
-    for rec in json.load(open(os.path.join(golden_dir, "ms_ssim.json")))[:2]:
+    recs = json.load(open(os.path.join(golden_dir, "ms_ssim.json")))
+    for rec in recs[:2] + recs[4:5]:       # [4]: 200x200, odd pyramid levels
         g = _g(rec["seed"])
         n, hw = rec["n"], rec["hw"]
         X = torch.rand(n, 3, hw, hw, generator=g)

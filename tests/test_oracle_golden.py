@@ -37,7 +37,7 @@ def test_param_inventory():
     assert g["u1.model.0.weight"].shape == (1024, 512, 3, 3) and g["c1.pwconv1.weight"].shape == (12, 3)
 
 
-@pytest.mark.parametrize("case", [0, 1])
+@pytest.mark.parametrize("case", [0, 1, 4])   # case 4: 200x200 -> odd pyramid levels (padded avg_pool, MS_SSIM.py:214-216)
 def test_ms_ssim_golden(golden_dir, case):
     rec = json.load(open(os.path.join(golden_dir, "ms_ssim.json")))[case]
     g = torch.Generator().manual_seed(rec["seed"])
