@@ -83,52 +83,64 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float2 f2dup(float v) { return make_float2(v, v); }
-// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) for two elements
-__device__ __forceinline__ float2 gelu_cdf_fast2(float2 x) {
-  float2 z = __fmul2_rn(x, f2dup(0.70710678118654752f));
-  z.x = fminf(fmaxf(z.x, -DS_ERF_ZM), DS_ERF_ZM);
-  z.y = fminf(fmaxf(z.y, -DS_ERF_ZM), DS_ERF_ZM);
-  const float2 t = __ffma2_rn(__fmul2_rn(z, z), f2dup(DS_ERF_A), f2dup(-1.0f));
-  float2 p = __ffma2_rn(f2dup(DS_ERF_C10), t, f2dup(DS_ERF_C9));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C8));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C7));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C6));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C5));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C4));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C3));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C2));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C1));
-  p = __ffma2_rn(p, t, f2dup(DS_ERF_C0));
-  const float2 hz = __fmul2_rn(z, f2dup(0.5f));
-  return __ffma2_rn(p, hz, f2dup(0.5f));      // 0.5 + 0.5 * z * P(t)
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)).  Scalar FFMAs with LITERAL coefficients: the Horner step p = p * t + c_i then has two
+// register operands and an immediate addend (SASS `FFMA R, R, R, imm`), which issues at the full 128 FMA/clk/SM.  The
+// packed form used in round 1 (FFMA2 with the coefficient as a third 64-bit register operand) is register-bandwidth bound at
+// ~78 FMA/clk/SM (scripts/micro/ffma2_rate.cu) -- it made the fused MLP epilogues ALU-bound 1.6x earlier than necessary.
+__device__ __forceinline__ float gelu_cdf_fast(float x) {
+  float z = x * 0.70710678118654752f;
+  z = fminf(fmaxf(z, -DS_ERF_ZM), DS_ERF_ZM);
+  const float t = fmaf(z * z, DS_ERF_A, -1.0f);
+  float p = fmaf(t, DS_ERF_C10, DS_ERF_C9);
+  p = fmaf(p, t, DS_ERF_C8);
+  p = fmaf(p, t, DS_ERF_C7);
+  p = fmaf(p, t, DS_ERF_C6);
+  p = fmaf(p, t, DS_ERF_C5);
+  p = fmaf(p, t, DS_ERF_C4);
+  p = fmaf(p, t, DS_ERF_C3);
+  p = fmaf(p, t, DS_ERF_C2);
+  p = fmaf(p, t, DS_ERF_C1);
+  p = fmaf(p, t, DS_ERF_C0);
+  return fmaf(p, z * 0.5f, 0.5f);      // 0.5 + 0.5 * z * P(t)
+}
+__device__ __forceinline__ float2 gelu_cdf_fast2(float2 x) { return make_float2(gelu_cdf_fast(x.x), gelu_cdf_fast(x.y)); }
+__device__ __forceinline__ float gelu_pdf_fast(float x) {
+  return 0.39894228040143268f * ex2_approx(x * x * -0.72134752044448170f);   // exp(-x^2/2) / sqrt(2 pi), one MUFU
 }
 __device__ __forceinline__ void gelu_parts_fast2(float2 x, float2& cdf, float2& pdf) {
   cdf = gelu_cdf_fast2(x);
-  const float2 a = __fmul2_rn(__fmul2_rn(x, x), f2dup(-0.72134752044448170f));   // -x^2/2 * log2(e)
-  pdf = __fmul2_rn(f2dup(0.39894228040143268f), make_float2(ex2_approx(a.x), ex2_approx(a.y)));
+  pdf = make_float2(gelu_pdf_fast(x.x), gelu_pdf_fast(x.y));
 }
 __device__ __forceinline__ void gelu_parts_fast(float x, float& cdf, float& pdf) {
-  float2 c, p;
-  gelu_parts_fast2(make_float2(x, x), c, p);
-  cdf = c.x; pdf = p.x;
+  cdf = gelu_cdf_fast(x);
+  pdf = gelu_pdf_fast(x);
 }
 // gelu'(x) = Phi(x) + x phi(x) directly: gelu'(x) - 0.5 is odd, = x * Q(t), t = 2 x^2 / 25 - 1, |x| clamped to 5 (beyond: 1 + 1e-5
 // and -1e-5 instead of 1 and 0), Q of degree 12; fp32 Horner error 9.8e-6 against float64.  No MUFU, ~19 issue slots per pair.
-__device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
-  float2 xc = make_float2(fminf(fmaxf(x.x, -5.0f), 5.0f), fminf(fmaxf(x.y, -5.0f), 5.0f));
-  const float2 t = __ffma2_rn(__fmul2_rn(xc, xc), f2dup(0.08f), f2dup(-1.0f));
-  const float q[13] = {1.421335801e-01f, -7.509966350e-02f, 6.658681821e-02f, -7.208436384e-02f, 8.015732403e-02f, -8.186698327e-02f, 8.084683210e-02f, -7.745690087e-02f, 5.105054164e-02f, -1.767319918e-02f, 1.795447979e-02f, -2.475356668e-02f, 1.020706059e-02f};
-  float2 p = __ffma2_rn(f2dup(q[12]), t, f2dup(q[11]));
-#pragma unroll
-  for (int i = 10; i >= 0; --i) p = __ffma2_rn(p, t, f2dup(q[i]));
-  return __ffma2_rn(p, xc, f2dup(0.5f));
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float xc = fminf(fmaxf(x, -5.0f), 5.0f);
+  const float t = fmaf(xc * xc, 0.08f, -1.0f);
+  float p = fmaf(t, 1.020706059e-02f, -2.475356668e-02f);
+  p = fmaf(p, t, 1.795447979e-02f);
+  p = fmaf(p, t, -1.767319918e-02f);
+  p = fmaf(p, t, 5.105054164e-02f);
+  p = fmaf(p, t, -7.745690087e-02f);
+  p = fmaf(p, t, 8.084683210e-02f);
+  p = fmaf(p, t, -8.186698327e-02f);
+  p = fmaf(p, t, 8.015732403e-02f);
+  p = fmaf(p, t, -7.208436384e-02f);
+  p = fmaf(p, t, 6.658681821e-02f);
+  p = fmaf(p, t, -7.509966350e-02f);
+  p = fmaf(p, t, 1.421335801e-01f);
+  return fmaf(p, xc, 0.5f);
 }
+__device__ __forceinline__ float2 gelu_grad_fast2(float2 x) { return make_float2(gelu_grad_fast(x.x), gelu_grad_fast(x.y)); }
 __device__ __forceinline__ float act_fwd_fast(int act, float v) {
-  if (act == ACT_GELU) return v * gelu_cdf_fast2(make_float2(v, v)).x;
+  if (act == ACT_GELU) return v * gelu_cdf_fast(v);
   return act_fwd(act, v);
 }
 __device__ __forceinline__ float act_bwd_fast(int act, float a) {
-  if (act == ACT_GELU) return gelu_grad_fast2(make_float2(a, a)).x;
+  if (act == ACT_GELU) return gelu_grad_fast(a);
   return act_bwd(act, a);
 }
 // (every non-GELU activation is written out branch-free under ONE uniform test of `act`: going through act_fwd()'s switch

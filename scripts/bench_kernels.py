@@ -205,6 +205,39 @@ def main():
             emit(out, "sc_conv k%ds%d %d->%d fwd+dgrad+wgrad+colsum" % (k, st, Ci, Co), ms2, bytes_=3 * io)
             del x
 
+    # ---- fused ConvNeXt Block MLP (csrc/fused_mlp.cu) at the four generator Blocks that use it, N = 16 -------------------
+    if want("mlp"):
+        L, st = ctx.L, ctx.stream
+        for name, M, cin, nout in (("uc4", 1048576, 128, 64), ("uc3", 262144, 256, 128), ("c2", 262144, 64, 128),
+                                   ("c3", 65536, 128, 256)):
+            hid = 4 * cin
+            T = torch.randn(M, cin, device="cuda", generator=g).bfloat16()
+            X = torch.randn(M, cin, device="cuda", generator=g).bfloat16()
+            dY = (torch.randn(M, nout, device="cuda", generator=g) * 0.1).bfloat16()
+            W1 = (torch.randn(hid, cin, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+            W2 = (torch.randn(nout, hid, device="cuda", generator=g) / hid ** 0.5).bfloat16()
+            Ws = (torch.randn(nout, cin, device="cuda", generator=g) / cin ** 0.5).bfloat16()
+            b1 = torch.randn(hid, device="cuda", generator=g) * 0.1
+            b2 = torch.randn(nout, device="cuda", generator=g) * 0.1
+            Y = torch.empty(M, nout, device="cuda", dtype=torch.bfloat16)
+            dT = torch.empty(M, cin, device="cuda", dtype=torch.bfloat16)
+            G = torch.empty(M, hid, device="cuda", dtype=torch.bfloat16)
+            A = torch.empty(M, hid, device="cuda", dtype=torch.bfloat16)
+            db1 = torch.zeros(hid, device="cuda")
+            fl_f = 2.0 * M * (cin * hid + hid * nout + cin * nout)
+            fl_b = 2.0 * M * (hid * nout + hid * cin)
+            ms = timeit(lambda: L.fused_mlp_fwd(T.data_ptr(), cin, X.data_ptr(), cin, M, cin, nout, W1.data_ptr(), b1.data_ptr(),
+                                                W2.data_ptr(), b2.data_ptr(), Ws.data_ptr(), Y.data_ptr(), nout, st))
+            emit(out, "fused_mlp_fwd %s M%d %d->%d->%d (+shortcut)" % (name, M, cin, hid, nout), ms, flops=fl_f,
+                 hbm_bytes=2 * M * (2 * cin + nout), hbm_bound_ms=round(2 * M * (2 * cin + nout) / PEAK["hbm_gbs"] / 1e6, 4))
+            ms = timeit(lambda: L.fused_mlp_bwd(T.data_ptr(), cin, dY.data_ptr(), nout, M, cin, nout, W1.data_ptr(), b1.data_ptr(),
+                                                W2.data_ptr(), dT.data_ptr(), cin, G.data_ptr(), A.data_ptr(), db1.data_ptr(), st))
+            nb = 2 * M * (2 * cin + nout + 2 * hid)
+            emit(out, "fused_mlp_bwd %s M%d %d->%d->%d (dT, G, A, db1; hidden recomputed)" % (name, M, cin, hid, nout), ms,
+                 flops=fl_b, hbm_bytes=nb, hbm_bound_ms=round(nb / PEAK["hbm_gbs"] / 1e6, 4),
+                 note="algorithmic FLOPs = the two input-gradient GEMMs; the recomputed pwconv1 earns no credit")
+            del T, X, dY, Y, dT, G, A
+
     # ---- config #5: generator-only inference, 32 x 512 x 512, bf16 ---------------------------------------------
     if want("infer"):
         from dsgan_b200.models import networks

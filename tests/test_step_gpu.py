@@ -19,6 +19,17 @@ def _g(seed):
     return torch.Generator().manual_seed(seed)
 
 
+def _record(kind, rec):
+    """Append the measured parity numbers to gpurun_out/parity.jsonl (evidence for profiles/; never read back)."""
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity.jsonl"), "a") as f:
+            f.write(json.dumps(dict(kind=kind, **rec)) + "\n")
+    except OSError:
+        pass
+
+
 def _grads_vs(P, ref_grads, tol, floor=2e-3):
     gmax = max(float(g.norm()) for g in ref_grads.values())
     bad = {}
@@ -274,8 +285,17 @@ def test_training_step_matches_oracle(prec, n, hw, bias, golden_dir):
         aF = rel(ac["fake_B"], ref["fake_B"])
         aD, aG = rel(_cat(ac["grads_D"]), _cat(ref["grads_D"])), rel(_cat(ac["grads_G"]), _cat(ref["grads_G"]))
         print("reference under bf16 autocast: fake_B %.2e  D grads %.2e  G grads %.2e" % (aF, aD, aG))
+        _record("train_step", dict(prec=prec, n=n, hw=hw, fake_B=eF, grads_D=eD, grads_G=eG, autocast_fake_B=aF,
+                                   autocast_grads_D=aD, autocast_grads_G=aG))
         assert eF < 3e-2 and eF < 1.5 * aF + 2e-3
-        assert eD < 1.5 * aD + 1e-2 and eG < 1.5 * aG + 1e-2
+        # G: north_star's 3e-2 at the benched configuration (16x256x256).  Before round 2 this was 5.5e-2, all of it noise in
+        # bias gradients that are structural zeros (biases feeding an InstanceNorm) -- now taken from fp32 sums.  Smaller
+        # batches average less: no worse than the reference's own bf16-autocast run.
+        assert eG < (3e-2 if n >= 16 else 1.5 * aG + 1e-2)
+        # D: bounded by conditioning, not by the kernels (profiles/r2_error_budget.json): D's gradient is the difference of
+        # the nearly cancelling real / fake branches, which amplifies fake_B's (in-tolerance) bf16 error 3-20x; with fake_B
+        # exact the same kernels give 5e-2, with D in fp32 6.5e-2.  Bar: no worse than the reference under bf16 autocast.
+        assert eD < 1.5 * aD + 1e-2
     if hw == 256 and n == 1 and prec == "fp32":  # the reference's own numbers for this exact configuration
         rec = [r for r in json.load(open(os.path.join(golden_dir, "train_step.json")))
                if r["hw"] == 256 and r["bias_std"] == bias][0]
