@@ -224,6 +224,34 @@ __global__ void k_add_n_v8(bf16* __restrict__ out, long long n8, const bf16* a, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Input pipeline on the device (data/aligned_dataset.py:53-90): decoded uint8 RGB images (H x W x 3, what PIL hands over)
+// -> transforms.ToTensor (x / 255) -> crop (h_off, w_off) -> Normalize(0.5, 0.5) -> horizontal flip -> optional RGB->gray,
+// written as the fp32 NCHW batch the model's set_input expects.  Same op order as the reference, so the result is bit-exact
+// with its CPU transforms; the host ships 1 byte per value instead of 4.
+__global__ void k_preprocess_u8(const unsigned char* __restrict__ src, int Hs, int Ws, const int* __restrict__ h_off,
+                                const int* __restrict__ w_off, const int* __restrict__ flip, float* __restrict__ dst,
+                                int C_out, int H, int W, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const long long r = i / W;
+    const int y = (int)(r % H);
+    const int n = (int)(r / H);
+    const int sx = (flip[n] ? (W - 1 - x) : x) + w_off[n], sy = y + h_off[n];
+    const unsigned char* p = src + (((long long)n * Hs + sy) * Ws + sx) * 3;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)p[c], 255.0f), 0.5f), 0.5f);
+    float* o = dst + ((long long)n * C_out * H + y) * W + x;
+    if (C_out == 3) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) o[(long long)c * H * W] = v[c];
+    } else {   // tmp = A[0]*0.299 + A[1]*0.587 + A[2]*0.114 (left to right, unfused like the reference's tensor ops)
+      o[0] = __fadd_rn(__fadd_rn(__fmul_rn(v[0], 0.299f), __fmul_rn(v[1], 0.587f)), __fmul_rn(v[2], 0.114f));
+    }
+  }
+}
+
 static inline int grid_for(long long n, int block, int cap = 148 * 16) {
   long long g = (n + block - 1) / block;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
@@ -307,5 +335,14 @@ int dsgan_scale_nc_bwd_apply(const void* dy, const float* s, const float* davg, 
   DS_DISPATCH_DT(dtype, (k_scale_nc_bwd_apply<T><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
                             (const T*)dy, s, davg, dmax, argmax, (T*)dx, HW, C, accumulate, total)));
   return DS_LAUNCHED("scale_nc_bwd_apply");
+}
+int dsgan_preprocess_u8(const unsigned char* src, int N, int Hs, int Ws, const int* h_off, const int* w_off, const int* flip,
+                        float* dst, int C_out, int H, int W, void* stream) {
+  DS_REQUIRE(C_out == 3 || C_out == 1, "preprocess_u8: C_out must be 3 or 1, got %d", C_out);
+  DS_REQUIRE(H >= 1 && W >= 1 && H <= Hs && W <= Ws, "preprocess_u8: crop %dx%d does not fit the %dx%d source", H, W, Hs, Ws);
+  const long long total = (long long)N * H * W;
+  k_preprocess_u8<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, Hs, Ws, h_off, w_off, flip, dst, C_out, H, W,
+                                                                         total);
+  return DS_LAUNCHED("preprocess_u8");
 }
 }

@@ -333,6 +333,21 @@ class Pix2PixModel(BaseModel):
                     return (L[SLOT["D_fake"]] + L[SLOT["D_real"]]) * 0.5
         raise AttributeError(name)
 
+    # ---- per-iteration monitoring without the extra generator forward -------------------------------
+    def batch_metrics(self):
+        """SSIM / PSNR of the step that just ran, from tensors it already produced: no second G forward, no image D2H.
+
+        The reference's loop (train.py:110-118) calls get_img_gen -- a full extra generator forward with the UPDATED
+        weights -- copies three images to the host and runs skimage on image 0 of the batch.  Here `ssim` is 1 - loss_ssim
+        (the Gaussian-window SSIM of (real_B, fake_B) over the whole batch that the loss kernel already reduced) and `psnr`
+        is 10 log10(255^2 / MSE) on the [0, 255]-scaled, clipped images of the whole batch.  These are monitoring values:
+        same quantities, not the same numbers as skimage's uniform-window SSIM of one post-update image."""
+        fake = (self.fake_B.detach().clamp(-1, 1) + 1) * 127.5
+        real = (self.real_B.clamp(-1, 1) + 1) * 127.5
+        mse = torch.mean((fake - real) ** 2)
+        psnr = 10.0 * torch.log10(255.0 ** 2 / torch.clamp(mse, min=1e-12))
+        return {"ssim": 1.0 - self._loss[SLOT["ssim"]], "psnr": psnr}
+
     # ---- host-side helpers of train.py (pix2pix_model.py:292-310) ----------------------------
     def get_img_tir(self, input):
         self.real_A = input["A"].to(self.device).float().contiguous()

@@ -48,6 +48,11 @@ int dsgan_nchw_to_nhwc(const float* src, void* dst, int dtype, int N, int C, int
 /* dst[n,c,y,x] (fp32) = alpha*src[n,y,x,c] (+ dst if accumulate). */
 int dsgan_nhwc_to_nchw(const void* src, int dtype, int ld_src, float* dst, int N, int C, int H, int W,
                        float alpha, int accumulate, void* stream);
+/* Device-side input pipeline (data/aligned_dataset.py:53-90): uint8 HWC RGB [N,Hs,Ws,3] -> ToTensor -> crop at
+ * (h_off[n], w_off[n]) -> Normalize(0.5,0.5) -> flip[n] (horizontal) -> fp32 NCHW [N,C_out,H,W]; C_out = 1 applies the
+ * reference's RGB->gray weights.  h_off / w_off / flip: int32 device arrays [N].  Bit-exact with the reference's CPU ops. */
+int dsgan_preprocess_u8(const unsigned char* src, int N, int Hs, int Ws, const int* h_off, const int* w_off, const int* flip,
+                        float* dst, int C_out, int H, int W, void* stream);
 /* dst[p, 0:C] (=|+=) src[p, 0:C] for npix pixels with independent pitches: torch.cat / slicing and their
  * backward (MixConvNeXtML.py:66,110). */
 int dsgan_copy_channels(const void* src, int ld_src, void* dst, int ld_dst, int dtype, long long npix, int C,

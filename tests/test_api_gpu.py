@@ -171,3 +171,21 @@ def test_gan_loss_modes(mode, real):
     losses.gan_loss(ctx, v, real, slot.data_ptr(), 1.0, 1.0, use_lsgan=mode != "bce", sigmoid_d=mode == "sigmoid_mse")
     assert abs(float(slot) - float(want)) < 1e-5
     assert rel(var_grad(v), xr.grad) < 1e-4
+
+
+def test_batch_metrics_reuse_the_step_outputs():
+    """N4: SSIM / PSNR from the tensors of the step that just ran (no extra generator forward)."""
+    import math
+    from dsgan_b200._lib import lib
+    m, _ = _model(["--precision", "fp32", "--cuda_graph", "0"])
+    A, B = O.synthetic_pair(2, 64, 64, seed=8)
+    m.set_input({"A": A, "B": B, "A_paths": [""], "B_paths": [""]})
+    m.optimize_parameters()
+    n0 = lib().cdll.dsgan_launch_count()
+    met = m.batch_metrics()
+    assert lib().cdll.dsgan_launch_count() == n0, "batch_metrics must not launch any network kernel"
+    fake, real = m.fake_B.cpu(), B
+    want_ssim = float(O.ssim((real + 1) / 2, (fake + 1) / 2, 1.0))
+    assert abs(float(met["ssim"]) - want_ssim) < 1e-4
+    mse = float((((fake.clamp(-1, 1) + 1) * 127.5 - (real + 1) * 127.5) ** 2).mean())
+    assert abs(float(met["psnr"]) - 10 * math.log10(255 ** 2 / mse)) < 1e-3
