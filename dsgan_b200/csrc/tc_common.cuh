@@ -146,6 +146,10 @@ __device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&w)[8]) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]),
                "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p) : "memory");
 }
+// vectorised fp32 reduction to global memory (sm_90+): one L2 atomic transaction for four consecutive floats (16-byte aligned)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

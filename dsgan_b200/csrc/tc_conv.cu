@@ -744,8 +744,9 @@ int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void*
   p.m_tiles = (d->Cg + BM - 1) / BM; p.n_tiles = (d->Cx + BN - 1) / BN;
   const int total_patches = d->N * p.tiles_y * p.tiles_x;
   const int base = d->ntaps * p.m_tiles * p.n_tiles;
-  int splits = (2 * sms() + base - 1) / base;
-  if (splits > total_patches) splits = total_patches;
+  // one wave of CTAs, at least 4 patches (8 k-blocks) per split: every split ends in a BM x BN fp32 atomic reduction
+  int splits = (sms() + base - 1) / base;
+  if (splits > total_patches / 4) splits = total_patches / 4;
   if (splits < 1) splits = 1;
   p.patches_per_split = (total_patches + splits - 1) / splits;
   p.splits = (total_patches + p.patches_per_split - 1) / p.patches_per_split;

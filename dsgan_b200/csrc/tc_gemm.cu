@@ -265,9 +265,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (row_ok && col0 < p.N) {
         if (MODE == 2) {
           float* o = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+          if (col0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            // 8 vector reductions instead of 32 scalar atomics: the split-K epilogue is bound by L2 atomic transactions
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
         } else {
           float f[32];
 #pragma unroll
@@ -430,9 +437,12 @@ int dsgan_tc_wgrad(const void* dY, int ld_dy, const void* X, int ld_x, long long
   p.M = Co; p.N = Ci; p.K = (int)P;
   p.m_tiles = (Co + BM - 1) / BM; p.n_tiles = (Ci + BN - 1) / BN;
   const int kb_total = (int)((P + BK - 1) / BK);
-  int splits = (num_sms() * 2) / (p.m_tiles * p.n_tiles);
+  // Split the pixel range so that ONE wave of CTAs covers the machine (every extra split costs a full BM x BN fp32 reduction
+  // into L2) and no split is shorter than 8 k-blocks: with the former 2 x SMs / tiles rule the small 1x1 layers (P = 16384,
+  // one or two output tiles) ran 256 one-k-block CTAs whose atomic epilogues took 60-70 us for 0.3 GFLOP.
+  int splits = num_sms() / (p.m_tiles * p.n_tiles);
+  if (splits > kb_total / 8) splits = kb_total / 8;
   if (splits < 1) splits = 1;
-  if (splits > kb_total) splits = kb_total;
   p.kb_per_split = (kb_total + splits - 1) / splits;
   p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;
   p.C = dW; p.ldc = ld_dw;

@@ -1,1 +1,3 @@
-for d in 79 207 143 128; do echo "DBG=$d"; DSGAN_MLP_DBG=$d python scripts/bench_kernels.py --only mlp --out gpurun_out/r2_k_dbg.jsonl 2>&1 | grep "bwd uc4\|bwd uc3" | cut -c1-130; done
+timeout 1200 python -m pytest tests/test_tc_gemm_gpu.py tests/test_kernels_gpu.py tests/test_step_gpu.py -x -q > gpurun_out/r2_t8.txt 2>&1; tail -4 gpurun_out/r2_t8.txt
+python bench.py --detail --steps 10 --no-cpu-baseline --no-extra > gpurun_out/r2_bench5.json 2> gpurun_out/r2_bench5.err; cut -c1-250 gpurun_out/r2_bench5.json
+grep "TF/s" gpurun_out/r2_bench5.err | grep "wgrad" | head -40
