@@ -399,12 +399,13 @@ __global__ void k_ca_bwd(const float* __restrict__ ds, const float* __restrict__
 // bf16 gradient tensor.  o = conv1x1(cat(dw_k(x))) + b_conv, then o * CA(o), then InstanceNorm:
 //   d b_conv[c]  = sum_n ( s[n,c] * S[n,c] + davg[n,c] + dmax[n,c] ),  S = sum_p of the norm's dx (fp32, ~0: dsgan_inorm_bwd_apply)
 //   d b_dw[c']   = sum_c W_conv[c,c'] * d b_conv[c]        (a depthwise bias shifts o by W_conv . b_dw)
-// one block; C <= 1024.
+// C / 32 blocks of 256 threads; C <= 4096.
 __global__ void k_mid_bias_grads(const float* __restrict__ S, const float* __restrict__ s, const float* __restrict__ davg,
                                  const float* __restrict__ dmax, int N, int C, const float* __restrict__ w,
                                  float* __restrict__ d_conv_bias, float* __restrict__ dq0, float* __restrict__ dq1,
                                  float* __restrict__ dq2, float* __restrict__ dq3) {
   extern __shared__ float db[];
+  // every block rebuilds the (tiny) conv-bias gradient; block b then owns the depthwise-bias entries [32 b, 32 b + 32)
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float a = 0.f;
     for (int n = 0; n < N; ++n) {
@@ -412,13 +413,19 @@ __global__ void k_mid_bias_grads(const float* __restrict__ S, const float* __res
       a += s[o] * S[o] + davg[o] + dmax[o];
     }
     db[c] = a;
-    atomicAdd(d_conv_bias + c, a);
+    if (blockIdx.x == 0) atomicAdd(d_conv_bias + c, a);
   }
   __syncthreads();
   const int q = C / 4;
-  for (int cp = threadIdx.x; cp < C; cp += blockDim.x) {
-    float a = 0.f;
-    for (int c = 0; c < C; ++c) a = fmaf(w[(long long)c * C + cp], db[c], a);
+  const int cp = blockIdx.x * 32 + (threadIdx.x & 31), part = threadIdx.x >> 5, nparts = blockDim.x >> 5;
+  float a = 0.f;
+  if (cp < C)
+    for (int c = part; c < C; c += nparts) a = fmaf(w[(long long)c * C + cp], db[c], a);   // coalesced along cp
+  __shared__ float red[8][33];
+  red[part][threadIdx.x & 31] = a;
+  __syncthreads();
+  if (part == 0 && cp < C) {
+    for (int i = 1; i < nparts; ++i) a += red[i][threadIdx.x & 31];
     float* dst = cp < q ? dq0 : (cp < 2 * q ? dq1 : (cp < 3 * q ? dq2 : dq3));
     atomicAdd(dst + (cp % q), a);
   }
@@ -430,8 +437,8 @@ int dsgan_mid_bias_grads(const float* dsum_nc, const float* s, const float* davg
                          const float* w_conv, float* d_conv_bias, float* d_b3, float* d_b5, float* d_b7, float* d_b9,
                          void* stream) {
   DS_REQUIRE(C % 4 == 0 && C <= 4096, "mid_bias_grads: bad C=%d", C);
-  k_mid_bias_grads<<<1, 256, sizeof(float) * C, (cudaStream_t)stream>>>(dsum_nc, s, davg, dmax, N, C, w_conv, d_conv_bias,
-                                                                      d_b3, d_b5, d_b7, d_b9);
+  k_mid_bias_grads<<<(C + 31) / 32, 256, sizeof(float) * C, (cudaStream_t)stream>>>(dsum_nc, s, davg, dmax, N, C, w_conv,
+                                                                                  d_conv_bias, d_b3, d_b5, d_b7, d_b9);
   return DS_LAUNCHED("mid_bias_grads");
 }
 int dsgan_maxpool_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int N, int H, int W, int C, int k,

@@ -737,8 +737,11 @@ def maxpool(ctx: Ctx, x: Var, k):
     return y
 
 
-def add_n(ctx: Ctx, xs):
-    """Sum of 2..5 same-shaped tensors (multi-scale skip sums, MixConvNeXtML.py:482-491)."""
+def add_n(ctx: Ctx, xs, share_grad=False):
+    """Sum of 2..5 same-shaped tensors (multi-scale skip sums, MixConvNeXtML.py:482-491).  `share_grad`: every addend is
+    consumed by this sum ONLY, so its gradient IS the sum's gradient: the addends alias the one gradient tensor instead of
+    receiving a copy each (22 copies per step).  Safe because backward kernels only read the gradient of their output; an
+    addend with a second consumer would accumulate into the shared buffer -- the caller vouches there is none."""
     x0 = xs[0]
     assert all(v.ld == v.C for v in xs)
     y = ctx.new(x0.N, x0.H, x0.W, x0.C)
@@ -750,8 +753,11 @@ def add_n(ctx: Ctx, xs):
         if gi is None:
             return
         for v in xs:
-            gp, gld, gacc = v.grad_out()
             assert v.fused_act is None
+            if share_grad and v.parent is None and v.g is None and y.g is not None:
+                v.g = y.g
+                continue
+            gp, gld, gacc = v.grad_out()
             ctx.copy_channels(gi, (gp, gld), v.npix, v.C, gacc)
     ctx.record(bwd)
     return y

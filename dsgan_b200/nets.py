@@ -221,13 +221,14 @@ def generator_forward(ctx: Ctx, P, x: Var) -> Var:
         for br, k, _cout in branches:
             scale = (x.H // src.H) * k          # total down-sampling w.r.t. the input
             lvl[scale].append(_downskip(ctx, P, "%s.%s" % (mod, br), src, k, pooled=p2 if k == 2 else None))
-    o = add_n(ctx, lvl[16])
+    # (every addend below -- Block outputs and down-skip branches -- is consumed by its sum only: gradients are shared)
+    o = add_n(ctx, lvl[16], share_grad=True)
     for (up, blk, _cin, _cout), skip, s in zip(specs.DEC, (R4, R3, R2, R1), (8, 4, 2, None)):
         o = _block(ctx, P, blk, _upsample(ctx, P, up + ".model.0", o, skip))
         if s is not None:
-            o = add_n(ctx, [o] + lvl[s])
+            o = add_n(ctx, [o] + lvl[s], share_grad=True)
     ctx.join(fk, keep=(x, loc))
-    return conv2d(ctx, add_n(ctx, [o, loc]), P["res.weight"], P["res.bias"], 3, pad=1)
+    return conv2d(ctx, add_n(ctx, [o, loc], share_grad=True), P["res.weight"], P["res.bias"], 3, pad=1)
 
 
 # ------------------------------------------------------------------------------------------------
