@@ -390,7 +390,7 @@ bool conv_try(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, 
   if (d->Ci == 1 && d->Co > 64) return false;   // (PatchGAN head's input-gradient 1 -> 256: measured faster on the tensor cores)
   // pointwise 64 -> 12 (block c1's pwconv2 input-gradient): eight lanes per pixel spend as long in the shuffle reduction as in
   // the FMAs; measured 0.275 ms here against 0.129 ms as a one-tap tcgen05 implicit GEMM with the narrow epilogue
-  if (narrow_out && d->nclass == 1 && d->ntaps[0] == 1 && d->Ci >= 64) return false;   // (PatchGAN head's input-gradient 1 -> 256: measured faster on the tensor cores)
+  if (narrow_out && d->nclass == 1 && d->ntaps[0] == 1 && d->Ci >= 64) return false;
   const long long quads = (long long)d->N * d->nclass * d->Hg * ((d->Wg + PT - 1) / PT);
   const int V = narrow_out ? (d->Co <= 4 ? 4 : (d->Co <= 8 ? 8 : 16)) : 8;   // channels per output vector
   const int cog = narrow_out ? 1 : (d->Co + 7) / 8;
