@@ -1,6 +1,7 @@
 // MaxPool2d(k) forward/backward and the CA channel-attention gate (global avg+max pooling, shared
 // fc1->PReLU->fc2, sigmoid) forward/backward.  Reference: MixConvNeXtML.py:5-22,68-74,333-354; vgg.py pools.
 #include "common.cuh"
+#include <string.h>
 #include "../../include/dsgan_b200.h"
 using namespace dsgan;
 
@@ -395,6 +396,190 @@ __global__ void k_ca_bwd(const float* __restrict__ ds, const float* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-scale max-pooling of ONE tensor: MaxPool2d(2), (4), (8), (16) of the same encoder skip (downSkip*: MixConvNeXtML.py:
+// 328-426, plus the encoder's own downSample :68-74 for k = 2) in one pass.  The separate kernels read R1 four times and
+// read-modify-write its gradient four times; here x is read once and dx written once.
+// A block owns 256 pixels = TB tiles of T x T (T = 2^NLEV) and up to 128 channels; level l is built from level l-1 in shared
+// memory (max is associative).  Backward carries (value, position) pairs: MaxPool2d routes the gradient to the FIRST maximum
+// in row-major scan order of each window, which inside a tile is the smallest code y*T + x among the maxima -- so merging the
+// four children with "greater value, or equal value and smaller code" reproduces the scan-order rule exactly.
+constexpr int MP_CH = 128;          // channels per block
+constexpr int MP_G = MP_CH / 8;
+
+struct MultiPoolParams {
+  const bf16* x; int ldx;
+  bf16* y[4];                      // outputs k = 2, 4, 8, 16 (dense, pitch C)
+  const bf16* dy[4];               // backward: gradients of those outputs (null = no gradient flowed)
+  bf16* dx; int lddx; int acc;
+  int N, H, W, C;
+  int tiles_x, tiles_y, total_tiles;
+};
+
+// 2x2 block b (0..63) of the block's pixel set -> tile slot, block coordinates inside the tile
+template <int NLEV>
+__device__ __forceinline__ void mp_locate(int b, int& slot, int& by, int& bx) {
+  constexpr int T = 1 << NLEV, NB = (T / 2) * (T / 2);
+  slot = b / NB;
+  const int r = b % NB;
+  by = r / (T / 2); bx = r % (T / 2);
+}
+
+template <int NLEV, bool BWD>
+__global__ void __launch_bounds__(256) k_multipool(const MultiPoolParams p) {
+  constexpr int T = 1 << NLEV, TB = 256 / (T * T);
+  extern __shared__ __align__(16) unsigned char mp_smem[];
+  // level arrays: windows per block at level l (1-based) = 256 >> (2 l); values bf16x8 per channel group, codes u8x8
+  uint4* sval[4]; uint2* spos[4];
+  {
+    unsigned char* q = mp_smem;
+    for (int l = 0; l < NLEV; ++l) { sval[l] = reinterpret_cast<uint4*>(q); q += (size_t)(64 >> (2 * l)) * MP_G * 16; }
+    for (int l = 0; l < NLEV; ++l) { spos[l] = reinterpret_cast<uint2*>(q); q += (size_t)(64 >> (2 * l)) * MP_G * 8; }
+  }
+  const int c_base = blockIdx.y * MP_CH;
+  const int G = min(MP_G, (p.C - c_base) / 8);
+  const int tile0 = blockIdx.x * TB;
+  // ---- level 1: 2x2 blocks straight from global memory ----
+  for (int item = threadIdx.x; item < 64 * G; item += 256) {
+    const int g = item % G, b = item / G;
+    int slot, by, bx;
+    mp_locate<NLEV>(b, slot, by, bx);
+    const int tile = tile0 + slot;
+    if (tile >= p.total_tiles) continue;
+    const int n = tile / (p.tiles_x * p.tiles_y), ty = (tile / p.tiles_x) % p.tiles_y, tx = tile % p.tiles_x;
+    const int y0 = ty * T + 2 * by, x0 = tx * T + 2 * bx, c0 = c_base + g * 8;
+    const bf16* xb = p.x + (((size_t)n * p.H + y0) * p.W + x0) * p.ldx + c0;
+    uint4 u[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) u[t] = __ldg(reinterpret_cast<const uint4*>(xb + ((size_t)(t >> 1) * p.W + (t & 1)) * p.ldx));
+    float m[8];
+    unsigned code[8];
+    unpack8p(u[0], m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) code[e] = (2 * by) * T + 2 * bx;
+#pragma unroll
+    for (int t = 1; t < 4; ++t) {
+      float v[8];
+      unpack8p(u[t], v);
+      const unsigned cd = (2 * by + (t >> 1)) * T + 2 * bx + (t & 1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (v[e] > m[e]) { m[e] = v[e]; code[e] = cd; }      // strict: the first maximum in scan order wins
+    }
+    const uint4 mv = pack8p(m);
+    sval[0][b * MP_G + g] = mv;
+    if (BWD) {
+      spos[0][b * MP_G + g] = make_uint2(code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24),
+                                         code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24));
+    } else {
+      const int Ho = p.H / 2, Wo = p.W / 2;
+      *reinterpret_cast<uint4*>(p.y[0] + (((size_t)n * Ho + y0 / 2) * Wo + x0 / 2) * p.C + c0) = mv;
+    }
+  }
+  __syncthreads();
+  // ---- levels 2 .. NLEV from shared memory ----
+#pragma unroll
+  for (int l = 1; l < NLEV; ++l) {
+    const int wpt = T >> (l + 1);                 // windows per tile side at this level
+    const int cpt = T >> l;                       // children per tile side
+    const int nwin = TB * wpt * wpt;
+    for (int item = threadIdx.x; item < nwin * G; item += 256) {
+      const int g = item % G, w = item / G;
+      const int slot = w / (wpt * wpt), wy = (w % (wpt * wpt)) / wpt, wx = w % wpt;
+      const int tile = tile0 + slot;
+      if (tile >= p.total_tiles) continue;
+      float m[8];
+      unsigned code[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int child = slot * cpt * cpt + (2 * wy + (t >> 1)) * cpt + 2 * wx + (t & 1);
+        float v[8];
+        unpack8p(sval[l - 1][child * MP_G + g], v);
+        unsigned cd[8];
+        if (BWD) {
+          const uint2 pc = spos[l - 1][child * MP_G + g];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { cd[e] = (pc.x >> (8 * e)) & 255u; cd[4 + e] = (pc.y >> (8 * e)) & 255u; }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (t == 0) { m[e] = v[e]; if (BWD) code[e] = cd[e]; }
+          else if (v[e] > m[e] || (BWD && v[e] == m[e] && cd[e] < code[e])) { m[e] = v[e]; if (BWD) code[e] = cd[e]; }
+        }
+      }
+      const uint4 mv = pack8p(m);
+      sval[l][w * MP_G + g] = mv;
+      if (BWD) {
+        spos[l][w * MP_G + g] = make_uint2(code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24),
+                                           code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24));
+      } else {
+        const int n = tile / (p.tiles_x * p.tiles_y), ty = (tile / p.tiles_x) % p.tiles_y, tx = tile % p.tiles_x;
+        const int k = 2 << l, Ho = p.H / k, Wo = p.W / k;
+        *reinterpret_cast<uint4*>(p.y[l] + (((size_t)n * Ho + ty * wpt + wy) * Wo + tx * wpt + wx) * p.C + c_base + g * 8) = mv;
+      }
+    }
+    __syncthreads();
+  }
+  if (!BWD) return;
+  // ---- backward: every pixel collects the gradient of each level whose window maximum it is ----
+  for (int item = threadIdx.x; item < 64 * G; item += 256) {
+    const int g = item % G, b = item / G;
+    int slot, by, bx;
+    mp_locate<NLEV>(b, slot, by, bx);
+    const int tile = tile0 + slot;
+    if (tile >= p.total_tiles) continue;
+    const int n = tile / (p.tiles_x * p.tiles_y), ty = (tile / p.tiles_x) % p.tiles_y, tx = tile % p.tiles_x;
+    const int c0 = c_base + g * 8;
+    float gr[4][8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gr[t][e] = 0.f;
+#pragma unroll
+    for (int l = 0; l < NLEV; ++l) {
+      if (p.dy[l] == nullptr) continue;
+      const int wpt = T >> (l + 1), k = 2 << l;
+      const int wy = by >> l, wx = bx >> l;                      // this 2x2 block's window at level l
+      const int w = slot * wpt * wpt + wy * wpt + wx;
+      const uint2 pc = spos[l][w * MP_G + g];
+      const int Ho = p.H / k, Wo = p.W / k;
+      float dv[8];
+      unpack8p(__ldg(reinterpret_cast<const uint4*>(p.dy[l] + (((size_t)n * Ho + ty * wpt + wy) * Wo + tx * wpt + wx) * p.C + c0)), dv);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const unsigned cd = (2 * by + (t >> 1)) * T + 2 * bx + (t & 1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const unsigned pe = ((e < 4 ? pc.x : pc.y) >> (8 * (e & 3))) & 255u;
+          if (pe == cd) gr[t][e] += dv[e];
+        }
+      }
+    }
+    bf16* db = p.dx + (((size_t)n * p.H + ty * T + 2 * by) * p.W + tx * T + 2 * bx) * p.lddx + c0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint4* o = reinterpret_cast<uint4*>(db + ((size_t)(t >> 1) * p.W + (t & 1)) * p.lddx);
+      if (p.acc) {
+        float old[8];
+        unpack8p(*o, old);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gr[t][e] += old[e];
+      }
+      *o = pack8p(gr[t]);
+    }
+  }
+}
+
+template <int NLEV, bool BWD>
+int launch_multipool(const MultiPoolParams& p, cudaStream_t s) {
+  constexpr int T = 1 << NLEV, TB = 256 / (T * T);
+  size_t smem = 0;
+  for (int l = 0; l < NLEV; ++l) smem += (size_t)(64 >> (2 * l)) * MP_G * 24;
+  dim3 grid((unsigned)((p.total_tiles + TB - 1) / TB), (unsigned)((p.C + MP_CH - 1) / MP_CH));
+  k_multipool<NLEV, BWD><<<grid, 256, smem, s>>>(p);
+  return DS_LAUNCHED(BWD ? "multipool_bwd" : "multipool_fwd");
+}
+
 // Bias gradients of a MidMLKA (MixConvNeXtML.py:109-117) from per-plane fp32 statistics instead of a sum over the rounded
 // bf16 gradient tensor.  o = conv1x1(cat(dw_k(x))) + b_conv, then o * CA(o), then InstanceNorm:
 //   d b_conv[c]  = sum_n ( s[n,c] * S[n,c] + davg[n,c] + dmax[n,c] ),  S = sum_p of the norm's dx (fp32, ~0: dsgan_inorm_bwd_apply)
@@ -474,6 +659,43 @@ int dsgan_maxpool_bwd(const void* x, int ld_x, const void* dy, int ld_dy, void* 
                             (const T*)x, ld_x, (const T*)dy, ld_dy, (T*)dx, ld_dx, H, W, C, k, accumulate, relu_mask,
                             total)));
   return DS_LAUNCHED("maxpool_bwd");
+}
+int dsgan_multipool_supported(int dtype, int H, int W, int C, int nlev, int ld_x) {
+  if (dtype != DT_BF16 || nlev < 2 || nlev > 4 || C % 8 || ld_x % 8) return 0;
+  const int T = 1 << nlev;
+  return (H % T == 0 && W % T == 0) ? 1 : 0;
+}
+static int multipool_fill(MultiPoolParams* p, const void* x, int ld_x, int N, int H, int W, int C, int nlev) {
+  memset(p, 0, sizeof(*p));
+  const int T = 1 << nlev;
+  p->x = (const bf16*)x; p->ldx = ld_x; p->N = N; p->H = H; p->W = W; p->C = C;
+  p->tiles_x = W / T; p->tiles_y = H / T; p->total_tiles = N * p->tiles_x * p->tiles_y;
+  return 0;
+}
+int dsgan_multipool_fwd(const void* x, int ld_x, void* y2, void* y4, void* y8, void* y16, int dtype, int N, int H, int W, int C,
+                        int nlev, void* stream) {
+  DS_REQUIRE(dsgan_multipool_supported(dtype, H, W, C, nlev, ld_x), "multipool_fwd: unsupported shape %dx%dx%d nlev=%d", H, W, C, nlev);
+  DS_REQUIRE(((uintptr_t)x % 16 == 0) && y2 && y4 && (nlev < 3 || y8) && (nlev < 4 || y16), "multipool_fwd: bad pointers");
+  MultiPoolParams p;
+  multipool_fill(&p, x, ld_x, N, H, W, C, nlev);
+  p.y[0] = (bf16*)y2; p.y[1] = (bf16*)y4; p.y[2] = (bf16*)y8; p.y[3] = (bf16*)y16;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nlev == 2) return launch_multipool<2, false>(p, s);
+  if (nlev == 3) return launch_multipool<3, false>(p, s);
+  return launch_multipool<4, false>(p, s);
+}
+int dsgan_multipool_bwd(const void* x, int ld_x, const void* dy2, const void* dy4, const void* dy8, const void* dy16, void* dx,
+                        int ld_dx, int accumulate, int dtype, int N, int H, int W, int C, int nlev, void* stream) {
+  DS_REQUIRE(dsgan_multipool_supported(dtype, H, W, C, nlev, ld_x) && ld_dx % 8 == 0, "multipool_bwd: unsupported shape");
+  DS_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)dx % 16 == 0), "multipool_bwd: unaligned");
+  MultiPoolParams p;
+  multipool_fill(&p, x, ld_x, N, H, W, C, nlev);
+  p.dy[0] = (const bf16*)dy2; p.dy[1] = (const bf16*)dy4; p.dy[2] = (const bf16*)dy8; p.dy[3] = (const bf16*)dy16;
+  p.dx = (bf16*)dx; p.lddx = ld_dx; p.acc = accumulate;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nlev == 2) return launch_multipool<2, true>(p, s);
+  if (nlev == 3) return launch_multipool<3, true>(p, s);
+  return launch_multipool<4, true>(p, s);
 }
 int dsgan_ca_fwd(const void* x, int dtype, int N, long long HW, int C, const float* fc1, const float* slope,
                  const float* fc2, float* avg, float* mx, int* argmax, float* s, void* workspace, void* stream) {

@@ -91,7 +91,7 @@ FAMILY = {"fused_mlp_fwd": "dense", "fused_mlp_bwd": "dense", "mid_bias_grads": 
           "tc_conv_wgrad": "dense", "pack_conv_weight": "optim", "pack_conv_weights": "optim",
           "colsum": "reduce", "dwconv_fwd": "dwconv", "dwconv_wgrad": "dwconv",
           "inorm_stats": "norm", "inorm_apply": "norm", "inorm_bwd_stats": "norm", "inorm_bwd_apply": "norm",
-          "maxpool_fwd": "pool", "maxpool_bwd": "pool", "ca_fwd": "ca", "ca_bwd": "ca", "scale_nc_fwd": "ca",
+          "maxpool_fwd": "pool", "maxpool_bwd": "pool", "multipool_fwd": "pool", "multipool_bwd": "pool", "ca_fwd": "ca", "ca_bwd": "ca", "scale_nc_fwd": "ca",
           "scale_nc_bwd_reduce": "ca", "scale_nc_bwd_apply": "ca",
           "gan_loss": "loss", "l1_loss": "loss", "tv_loss": "loss", "ssim_fwd": "ssim", "ssim_bwd": "ssim",
           "avgpool2_fwd": "ssim", "avgpool2_bwd": "ssim", "msssim_combine": "ssim", "ssim_combine": "ssim",
@@ -735,6 +735,30 @@ def maxpool(ctx: Ctx, x: Var, k):
         ctx.L.maxpool_bwd(x.ptr, x.ld, gi[0], gi[1], gp, gld, ctx.dt, x.N, x.H, x.W, x.C, k, gacc, relu, ctx.stream)
     ctx.record(bwd)
     return y
+
+
+def multi_maxpool(ctx: Ctx, x: Var, nlev):
+    """[MaxPool2d(2)(x), MaxPool2d(4)(x), ... MaxPool2d(2**nlev)(x)] in one pass over x, and one combined backward pass
+    (the multi-scale down-skips of an encoder stage, MixConvNeXtML.py:328-426, share their input with the stage's own
+    downSample).  Falls back to separate pooling kernels where the fused kernel does not apply (fp32 mode)."""
+    if nlev < 2 or not ctx.L.cdll.dsgan_multipool_supported(ctx.dt, x.H, x.W, x.C, nlev, x.ld) or x.ptr % 16:
+        return [maxpool(ctx, x, 2 << l) for l in range(nlev)]
+    ys = [ctx.new(x.N, x.H >> (l + 1), x.W >> (l + 1), x.C) for l in range(nlev)]
+    yp = [y.ptr for y in ys] + [None] * (4 - nlev)
+    _label(ctx, x, "k2..%d" % (1 << nlev))
+    ctx.L.multipool_fwd(x.ptr, x.ld, yp[0], yp[1], yp[2], yp[3], ctx.dt, x.N, x.H, x.W, x.C, nlev, ctx.stream)
+
+    def bwd():
+        gis = [y.grad_in() for y in ys]
+        if all(g is None for g in gis):
+            return
+        assert all(g is None or g[1] == x.C for g in gis) and x.fused_act is None
+        gp, gld, gacc = x.grad_out()
+        g = [gi[0] if gi is not None else None for gi in gis] + [None] * (4 - nlev)
+        _label(ctx, x, "k2..%d" % (1 << nlev))
+        ctx.L.multipool_bwd(x.ptr, x.ld, g[0], g[1], g[2], g[3], gp, gld, gacc, ctx.dt, x.N, x.H, x.W, x.C, nlev, ctx.stream)
+    ctx.record(bwd)
+    return ys
 
 
 def add_n(ctx: Ctx, xs, share_grad=False):

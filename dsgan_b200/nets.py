@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from . import specs
 from .engine import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, Ctx, Param, Var, add_n, block_mlp, ca_scale, concat_into,
-                     conv2d, conv_transpose2d, dwconv, fused_mlp_ok, image_to_nhwc, inorm, maxpool)
+                     conv2d, conv_transpose2d, dwconv, fused_mlp_ok, image_to_nhwc, inorm, maxpool, multi_maxpool)
 
 
 class ParamTree(nn.Module):
@@ -210,17 +210,18 @@ def generator_forward(ctx: Ctx, P, x: Var) -> Var:
         if i < 4:   # R1..R4 are the decoder's skip tensors: write them straight into channels [C, 2C) of its concat buffer
             out = ctx.new(x.N, x.H >> i, x.W >> i, 2 * cout).slice(cout, cout)
         if i > 0:
-            t = maxpool(ctx, t, 2)
-            pools.append(t)     # MaxPool2d(2)(R_i): also the input of R_i's first down-skip branch
+            t = pools[-1][0]    # MaxPool2d(2)(R_i): the encoder's downSample, also the input of R_i's first down-skip branch
         t = _block(ctx, P, name, t, out=out, need_dx=i > 0)
         R.append(t)
+        if i < 4:   # every pooled view of R_{i+1} the down-skips need (k = 2 .. 2^(4-i)) in ONE pass over it
+            pools.append(multi_maxpool(ctx, t, 4 - i))
     R1, R2, R3, R4, R5 = R
     # pyramid[level] collects the down-skip tensors landing on that decoder level
     lvl = {16: [R5], 8: [], 4: [], 2: []}
-    for (mod, _cin, branches), src, p2 in zip(specs.SKIPS, (R1, R2, R3, R4), pools):
+    for (mod, _cin, branches), src, pl in zip(specs.SKIPS, (R1, R2, R3, R4), pools):
         for br, k, _cout in branches:
             scale = (x.H // src.H) * k          # total down-sampling w.r.t. the input
-            lvl[scale].append(_downskip(ctx, P, "%s.%s" % (mod, br), src, k, pooled=p2 if k == 2 else None))
+            lvl[scale].append(_downskip(ctx, P, "%s.%s" % (mod, br), src, k, pooled=pl[k.bit_length() - 2]))
     # (every addend below -- Block outputs and down-skip branches -- is consumed by its sum only: gradients are shared)
     o = add_n(ctx, lvl[16], share_grad=True)
     for (up, blk, _cin, _cout), skip, s in zip(specs.DEC, (R4, R3, R2, R1), (8, 4, 2, None)):

@@ -225,6 +225,15 @@ int dsgan_maxpool_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int
 /* dx (=|+=) dy routed to the first maximum in scan order; if relu_mask, the result is then multiplied by (x>0). */
 int dsgan_maxpool_bwd(const void* x, int ld_x, const void* dy, int ld_dy, void* dx, int ld_dx, int dtype, int N,
                       int H, int W, int C, int k, int accumulate, int relu_mask, void* stream);
+/* MaxPool2d(2), (4), ... (2^nlev) of ONE bf16 NHWC tensor in a single pass (nlev = 2..4), and the combined backward:
+ * the multi-scale down-skips of an encoder stage (MixConvNeXtML.py:328-426) plus its own downSample (:68-74).  Outputs /
+ * output-gradients are dense (pitch C); a NULL dy means no gradient flowed into that scale.  Same first-maximum routing as
+ * nn.MaxPool2d.  dx (=|+=). */
+int dsgan_multipool_supported(int dtype, int H, int W, int C, int nlev, int ld_x);
+int dsgan_multipool_fwd(const void* x, int ld_x, void* y2, void* y4, void* y8, void* y16, int dtype, int N, int H, int W, int C,
+                        int nlev, void* stream);
+int dsgan_multipool_bwd(const void* x, int ld_x, const void* dy2, const void* dy4, const void* dy8, const void* dy16, void* dx,
+                        int ld_dx, int accumulate, int dtype, int N, int H, int W, int C, int nlev, void* stream);
 /* AdaptiveAvgPool2d(1) + AdaptiveMaxPool2d(1) + fc1 -> PReLU -> fc2 (shared) -> add -> sigmoid
  * (CA.forward, MixConvNeXtML.py:17-22).  avg,mx,s: fp32 [N,C]; argmax int32 [N,C] (pixel index);
  * fc1 [C/8,C], fc2 [C,C/8], slope [1]. */

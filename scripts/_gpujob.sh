@@ -1,1 +1,4 @@
-for v in "1 1" "1 0" "0 1"; do set -- $v; echo "SC_IN=$1 SC_OUT=$2"; DSGAN_SC_IN=$1 DSGAN_SC_OUT=$2 python bench.py --detail --steps 5 --no-cpu-baseline --no-extra 2> gpurun_out/r2_sc.err | cut -c1-160; grep "TF/s" gpurun_out/r2_sc.err | grep -E " (3|6|12|1)->|->(3|6|12|1) " | head -24; done
+timeout 900 python -m pytest tests/test_kernels_gpu.py -x -q -k "multi_maxpool or maxpool" > gpurun_out/r2_t10.txt 2>&1; tail -15 gpurun_out/r2_t10.txt
+timeout 1200 python -m pytest tests/test_step_gpu.py -x -q > gpurun_out/r2_t11.txt 2>&1; tail -4 gpurun_out/r2_t11.txt
+python bench.py --detail --steps 10 --no-cpu-baseline --no-extra > gpurun_out/r2_bench7.json 2> gpurun_out/r2_bench7.err; cut -c1-250 gpurun_out/r2_bench7.json
+grep "TF/s" gpurun_out/r2_bench7.err | grep -i "pool" | head

@@ -270,3 +270,42 @@ def test_adam_matches_torch():
         ctx.L.adam_step(pc.data_ptr(), gc.data_ptr(), m.data_ptr(), v.data_ptr(), 1000, 2e-4, 0.5, 0.999, 1e-8, t, 0.25,
                         None, ctx.stream)
     assert rel(pc.cpu(), p.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("nlev,C,H,W", [(4, 64, 32, 48), (3, 128, 16, 24), (2, 256, 8, 12), (4, 136, 16, 16)])
+@pytest.mark.parametrize("ties", [False, True])
+def test_multi_maxpool_matches_separate_pools(nlev, C, H, W, ties):
+    """MaxPool2d(2..2^nlev) of one tensor in a single pass + the combined backward, against torch (first-maximum routing,
+    SURVEY Q5) -- with heavily tied inputs too (small integers in bf16), where the scan-order rule decides the routing.  The
+    input is a channel slice of a wider buffer and its gradient accumulates onto an existing one, like R1..R4 in the generator."""
+    ctx = ctx_for("bf16")
+    g = _g(7 + nlev + C)
+    x = torch.randint(-3, 4, (2, C, H, W), generator=g).float() if ties else q(torch.randn(2, C, H, W, generator=g), "bf16")
+    xr = x.clone().requires_grad_(True)
+    outs = [F.max_pool2d(xr, 2 << l) for l in range(nlev)]
+    dys = [q(torch.randn(o.shape, generator=g), "bf16") for o in outs]
+    if nlev >= 3:
+        dys[1] = None                      # one scale without any gradient
+    torch.autograd.backward([o for o, d in zip(outs, dys) if d is not None], [d for d in dys if d is not None])
+    base = q(torch.randn(2, C, H, W, generator=g), "bf16")
+    wide = ctx.new(2, H, W, 2 * C)
+    wide.t.zero_()
+    xv = wide.slice(C, C)
+    wide.t[..., C:] = x.permute(0, 2, 3, 1).to("cuda", ctx.tdtype)
+    ys = E.multi_maxpool(ctx, xv, nlev)
+    assert len(ys) == nlev
+    for y, o in zip(ys, outs):
+        assert torch.equal(var_data(y), o.detach())
+    for y, d in zip(ys, dys):
+        if d is not None:
+            set_grad(ctx, y, d)
+    # pre-existing gradient on the slice: the pooling backward must accumulate
+    wide.g = torch.zeros((2, H, W, 2 * C), dtype=ctx.tdtype, device="cuda")
+    wide.g[..., C:] = base.permute(0, 2, 3, 1).to("cuda", ctx.tdtype)
+    ctx.backward()
+    got = wide.g[..., C:].float().cpu().permute(0, 3, 1, 2)
+    want = q(base + xr.grad, "bf16")
+    assert rel(got, want) < 4e-3
+    assert float((wide.g[..., :C].float().abs()).max()) == 0.0
+    if ties:   # routing must agree element for element (sums of bf16 values: compare where a gradient landed)
+        assert torch.equal((got - base) != 0, xr.grad != 0) or rel(got, want) < 1e-3
