@@ -122,6 +122,7 @@ __global__ void k_tv(const float* __restrict__ x, int H, int W, long long total,
 }
 
 #include "ssim_v2.cuh"
+#include "ssim_v3.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // (first-generation kernels, kept as the readable reference of the tiling; the ABI dispatches to ssim_v2.cuh)
@@ -390,29 +391,54 @@ int dsgan_tv_loss(const float* x, int NC, int H, int W, float denom, float* loss
   k_tv<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, H, W, total, 1.0f / denom, loss, grad_scale, dx);
   return DS_LAUNCHED("tv_loss");
 }
-int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, float* sums,
+// segment length / task count of the row-streaming kernels: enough warps to fill the machine, segments >= 16 rows (10 warm-up rows each)
+static void ssim_tasks(int NC, int rows, int cols, int* nstrip, int* nseg, int* rs, long long* ntasks) {
+  *nstrip = (cols + SS_W - 1) / SS_W;
+  long long per = (long long)NC * *nstrip;
+  int want = (int)((2368 + per - 1) / per);   // 16 warps per SM
+  int maxseg = (rows + 15) / 16;
+  if (want > maxseg) want = maxseg;
+  if (want < 1) want = 1;
+  *rs = (rows + want - 1) / want;
+  *nseg = (rows + *rs - 1) / *rs;
+  *ntasks = per * *nseg;
+}
+int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, float* sums, float* moments,
                    void* stream) {
   DS_REQUIRE(H >= 11 && W >= 11, "ssim: image %dx%d smaller than the 11-tap window", H, W);
   DS_REQUIRE(NC <= 65535, "ssim: too many planes (%d)", NC);
   if (ensure_window()) return 1;
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * NC, s);
-  dim3 grid(cdiv(W - HALO, TS), cdiv(H - HALO, TS), NC);
-  k_ssim_fwd2<<<grid, 256, 0, s>>>(X, Y, H, W, C1, C2, sums);
+  int nstrip, nseg, rs;
+  long long ntasks;
+  ssim_tasks(NC, H - 10, W - 10, &nstrip, &nseg, &rs, &ntasks);
+  const unsigned blocks = (unsigned)((ntasks + SS_WARPS - 1) / SS_WARPS);
+  if (moments) k_ssim_fwd3<true><<<blocks, 32 * SS_WARPS, 0, s>>>(X, Y, H, W, C1, C2, sums, moments, NC, nstrip, nseg, rs, ntasks);
+  else k_ssim_fwd3<false><<<blocks, 32 * SS_WARPS, 0, s>>>(X, Y, H, W, C1, C2, sums, nullptr, NC, nstrip, nseg, rs, ntasks);
   return DS_LAUNCHED("ssim_fwd");
 }
 int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, const float* coef,
-                   float* dY, int accumulate, void* stream) {
+                   const float* moments, float* dY, int accumulate, void* stream) {
   DS_REQUIRE(H >= 11 && W >= 11, "ssim: image %dx%d smaller than the 11-tap window", H, W);
   DS_REQUIRE(NC <= 65535, "ssim: too many planes (%d)", NC);
   if (ensure_window()) return 1;
+  if (moments) {   // from the moments the forward pass stored: row-streaming transposed filter (ssim_v3.cuh)
+    int nstrip, nseg, rs;
+    long long ntasks;
+    ssim_tasks(NC, H, W, &nstrip, &nseg, &rs, &ntasks);
+    const unsigned blocks = (unsigned)((ntasks + SS_WARPS - 1) / SS_WARPS);
+    k_ssim_bwd3<<<blocks, 32 * SS_WARPS, 0, (cudaStream_t)stream>>>(X, Y, moments, H, W, C1, C2, coef, dY, accumulate, NC, nstrip,
+                                                                     nseg, rs, ntasks);
+    return DS_LAUNCHED("ssim_bwd");
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_ssim_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd2Smem));
     if (e != cudaSuccess) { set_error("ssim_bwd smem attr: %s", cudaGetErrorString(e)); return 1; }
     attr_set = true;
   }
-  dim3 grid(cdiv(W, TS), cdiv(H, TS), NC);
+  dim3 grid(cdiv(W, V_TS), cdiv(H, V_TS), NC);
   k_ssim_bwd2<<<grid, 256, sizeof(Bwd2Smem), (cudaStream_t)stream>>>(X, Y, H, W, C1, C2, coef, dY, accumulate);
   return DS_LAUNCHED("ssim_bwd");
 }

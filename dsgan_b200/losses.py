@@ -31,13 +31,15 @@ def _workspace(X, levels, want):
     ws = _WORK.get(key)
     if ws is None:
         f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=X.device)
-        ws = {"sums": f(levels, N * C, 2), "coef": f(levels, N * C, 2) if want else None, "px": [], "py": [], "g": []}
+        ws = {"sums": f(levels, N * C, 2), "coef": f(levels, N * C, 2) if want else None, "px": [], "py": [], "g": [],
+              "mom": [f(5, N * C, H - 10, W - 10)] if want else [None]}   # filtered moments per level (forward -> backward)
         h, w = H, W
         for lv in range(1, levels):
             h, w = h // 2 + h % 2, w // 2 + w % 2   # avg_pool2d(kernel 2, padding = side % 2), MS_SSIM.py:214-216
             ws["px"].append(f(N, C, h, w))
             ws["py"].append(f(N, C, h, w))
             ws["g"].append(f(N, C, h, w) if want else None)
+            ws["mom"].append(f(5, N * C, h - 10, w - 10) if want else None)
         _WORK[key] = ws
     return ws
 
@@ -109,7 +111,9 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
     xs, ys, sizes = [X], [Y], []
     for lv in range(levels):
         h, w = xs[lv].shape[-2:]
-        L_.ssim_fwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, sums[lv].data_ptr(), ctx.stream)
+        mom = ws["mom"][lv]
+        L_.ssim_fwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, sums[lv].data_ptr(),
+                    mom.data_ptr() if mom is not None else None, ctx.stream)
         sizes.append((h - 10) * (w - 10))
         if lv < levels - 1:
             nx, ny = ws["px"][lv], ws["py"][lv]
@@ -132,7 +136,7 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
     for lv in reversed(range(levels)):
         h, w = xs[lv].shape[-2:]
         g = dY if lv == 0 else ws["g"][lv - 1]
-        L_.ssim_bwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, coef[lv].data_ptr(), g.data_ptr(),
+        L_.ssim_bwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, coef[lv].data_ptr(), ws["mom"][lv].data_ptr(), g.data_ptr(),
                     1 if lv == 0 else 0, ctx.stream)
         if g_next is not None:
             L_.avgpool2_bwd(g_next.data_ptr(), g.data_ptr(), NC, h, w, 1, ctx.stream)

@@ -263,15 +263,16 @@ int dsgan_l1_loss(const void* a, const void* b, int dtype, long long n, float* l
 /* TV loss (pix2pix_model.py:189-191) on NCHW fp32: loss[0] += (sum|dx|+sum|dy|)/denom; dx (+=) grad_scale*d/dx. */
 int dsgan_tv_loss(const float* x, int NC, int H, int W, float denom, float* loss, float grad_scale, float* dx,
                   void* stream);
-/* _ssim (MS_SSIM.py:55-92) on NCHW fp32 planes, 11-tap Gaussian, valid padding.
- * sums[nc] = {sum ssim_map, sum cs_map} (fp32 [NC,2], overwritten). X is the first argument of the reference
- * call (real), Y the second (fake). */
-int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, float* sums,
+/* sums[nc] = {sum over the valid windows of ssim_map, of cs_map} (fp32 [NC,2], overwritten) for X, Y: [NC,H,W] fp32 planes;
+ * 11-tap sigma 1.5 Gaussian, valid padding (MS_SSIM.py:26-92).  moments (optional, fp32 [5][NC][H-10][W-10]) receives the
+ * five filtered moments mu1, mu2, E[xx], E[yy], E[xy] of every window for the backward pass. */
+int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, float* sums, float* moments,
                    void* stream);
-/* dY (=|+=) sum over windows of coef[nc]={g_ssim,g_cs} . d{ssim_map,cs_map}/dY (coef: fp32 [NC,2], already
- * divided by the map size). */
+/* dY (=|+=) coef[nc,0] * d sum(ssim_map)/dY + coef[nc,1] * d sum(cs_map)/dY  (gradient w.r.t. the second argument only, as
+ * the training call needs it, pix2pix_model.py:193-195).  moments = the buffer dsgan_ssim_fwd filled for the same X, Y, or
+ * NULL (the moments are then recomputed on a halo: slower). */
 int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, const float* coef,
-                   float* dY, int accumulate, void* stream);
+                   const float* moments, float* dY, int accumulate, void* stream);
 /* F.avg_pool2d(k=2) on NCHW fp32 planes (MS_SSIM.py:214-216) and its backward (dx += dy/4). */
 int dsgan_avgpool2_fwd(const float* x, float* y, int NC, int H, int W, void* stream);
 int dsgan_avgpool2_bwd(const float* dy, float* dx, int NC, int H, int W, int accumulate, void* stream);
