@@ -303,6 +303,32 @@ __global__ void k_avgpool2_fwd(const float* __restrict__ x, float* __restrict__ 
     y[i] = 0.25f * a;
   }
 }
+// the X and the Y plane sets of one pyramid level in one launch
+__global__ void k_avgpool2_fwd_pair(const float* __restrict__ x1, float* __restrict__ y1, const float* __restrict__ x2,
+                                    float* __restrict__ y2, int H, int W, long long total) {
+  const int ph = H & 1, pw = W & 1, Ho = H / 2 + ph, Wo = W / 2 + pw;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < 2 * total; j += (long long)gridDim.x * blockDim.x) {
+    const bool second = j >= total;
+    const long long i = second ? j - total : j;
+    const float* x = second ? x2 : x1;
+    float* y = second ? y2 : y1;
+    const int ox = (int)(i % Wo);
+    const long long r = i / Wo;
+    const int oy = (int)(r % Ho);
+    const long long nc = r / Ho;
+    const int y0 = 2 * oy - ph, x0 = 2 * ox - pw;
+    const float* p = x + nc * H * W;
+    float a = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = y0 + dy, xx = x0 + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) a += p[(long long)yy * W + xx];
+      }
+    y[i] = 0.25f * a;
+  }
+}
 __global__ void k_avgpool2_bwd(const float* __restrict__ dy, float* __restrict__ dx, int H, int W, int accum,
                                long long total) {
   const int ph = H & 1, pw = W & 1, Ho = H / 2 + ph, Wo = W / 2 + pw;
@@ -367,6 +393,38 @@ inline int grid_for(long long n, int block, int cap = 148 * 8) {
 }
 }  // namespace
 
+// Row segments of the row-streaming kernels.  Every segment pays 10 warm-up rows, and the launch runs in waves of `slots`
+// resident warps: pick the segment count that minimises waves x (rows per segment + 10).  (A fixed "two segments" choice put
+// 3072 warps on 2960 slots -- two waves, the second 4 % full.)
+template <typename K>
+static int ssim_slots(K kern, int* cache) {
+  if (*cache == 0) {
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * SS_WARPS, 0);
+    *cache = sms * (occ > 0 ? occ : 1) * SS_WARPS;
+  }
+  return *cache;
+}
+static void ssim_tasks(int NC, int rows, int cols, int slots, int* nstrip, int* nseg, int* rs, long long* ntasks) {
+  *nstrip = (cols + SS_W - 1) / SS_W;
+  const long long per = (long long)NC * *nstrip;
+  int maxseg = rows / 16;
+  if (maxseg < 1) maxseg = 1;
+  if (maxseg > 64) maxseg = 64;
+  long long best = -1;
+  int best_n = 1;
+  for (int n = 1; n <= maxseg; ++n) {
+    const long long waves = (per * n + slots - 1) / slots;
+    const long long cost = waves * ((rows + n - 1) / n + 10);
+    if (best < 0 || cost < best) { best = cost; best_n = n; }
+  }
+  *rs = (rows + best_n - 1) / best_n;
+  *nseg = (rows + *rs - 1) / *rs;
+  *ntasks = per * *nseg;
+}
+
 extern "C" {
 int dsgan_gan_loss(const void* pred, int dtype, long long n, int ld, float target, int mode, float loss_scale,
                    float* loss, float grad_scale, void* dpred, void* stream) {
@@ -391,18 +449,6 @@ int dsgan_tv_loss(const float* x, int NC, int H, int W, float denom, float* loss
   k_tv<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, H, W, total, 1.0f / denom, loss, grad_scale, dx);
   return DS_LAUNCHED("tv_loss");
 }
-// segment length / task count of the row-streaming kernels: enough warps to fill the machine, segments >= 16 rows (10 warm-up rows each)
-static void ssim_tasks(int NC, int rows, int cols, int* nstrip, int* nseg, int* rs, long long* ntasks) {
-  *nstrip = (cols + SS_W - 1) / SS_W;
-  long long per = (long long)NC * *nstrip;
-  int want = (int)((2368 + per - 1) / per);   // 16 warps per SM
-  int maxseg = (rows + 15) / 16;
-  if (want > maxseg) want = maxseg;
-  if (want < 1) want = 1;
-  *rs = (rows + want - 1) / want;
-  *nseg = (rows + *rs - 1) / *rs;
-  *ntasks = per * *nseg;
-}
 int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, float* sums, float* moments,
                    void* stream) {
   DS_REQUIRE(H >= 11 && W >= 11, "ssim: image %dx%d smaller than the 11-tap window", H, W);
@@ -412,26 +458,30 @@ int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * NC, s);
   int nstrip, nseg, rs;
   long long ntasks;
-  ssim_tasks(NC, H - 10, W - 10, &nstrip, &nseg, &rs, &ntasks);
+  static int slots_s = 0, slots_n = 0;
+  ssim_tasks(NC, H - 10, W - 10, moments ? ssim_slots(k_ssim_fwd3<true>, &slots_s) : ssim_slots(k_ssim_fwd3<false>, &slots_n),
+             &nstrip, &nseg, &rs, &ntasks);
   const unsigned blocks = (unsigned)((ntasks + SS_WARPS - 1) / SS_WARPS);
   if (moments) k_ssim_fwd3<true><<<blocks, 32 * SS_WARPS, 0, s>>>(X, Y, H, W, C1, C2, sums, moments, NC, nstrip, nseg, rs, ntasks);
   else k_ssim_fwd3<false><<<blocks, 32 * SS_WARPS, 0, s>>>(X, Y, H, W, C1, C2, sums, nullptr, NC, nstrip, nseg, rs, ntasks);
   return DS_LAUNCHED("ssim_fwd");
 }
 int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, const float* coef,
-                   const float* moments, float* dY, int accumulate, void* stream) {
+                   const float* moments, float* dY, int accumulate, const float* gnext, void* stream) {
   DS_REQUIRE(H >= 11 && W >= 11, "ssim: image %dx%d smaller than the 11-tap window", H, W);
   DS_REQUIRE(NC <= 65535, "ssim: too many planes (%d)", NC);
   if (ensure_window()) return 1;
   if (moments) {   // from the moments the forward pass stored: row-streaming transposed filter (ssim_v3.cuh)
     int nstrip, nseg, rs;
     long long ntasks;
-    ssim_tasks(NC, H, W, &nstrip, &nseg, &rs, &ntasks);
+    static int slots_b = 0;
+    ssim_tasks(NC, H, W, ssim_slots(k_ssim_bwd3, &slots_b), &nstrip, &nseg, &rs, &ntasks);
     const unsigned blocks = (unsigned)((ntasks + SS_WARPS - 1) / SS_WARPS);
-    k_ssim_bwd3<<<blocks, 32 * SS_WARPS, 0, (cudaStream_t)stream>>>(X, Y, moments, H, W, C1, C2, coef, dY, accumulate, NC, nstrip,
-                                                                     nseg, rs, ntasks);
+    k_ssim_bwd3<<<blocks, 32 * SS_WARPS, 0, (cudaStream_t)stream>>>(X, Y, moments, H, W, C1, C2, coef, dY, accumulate, gnext, NC,
+                                                                     nstrip, nseg, rs, ntasks);
     return DS_LAUNCHED("ssim_bwd");
   }
+  DS_REQUIRE(gnext == nullptr, "ssim_bwd: the fused avg_pool adjoint needs the stored moments");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_ssim_bwd2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Bwd2Smem));
@@ -441,6 +491,11 @@ int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C
   dim3 grid(cdiv(W, V_TS), cdiv(H, V_TS), NC);
   k_ssim_bwd2<<<grid, 256, sizeof(Bwd2Smem), (cudaStream_t)stream>>>(X, Y, H, W, C1, C2, coef, dY, accumulate);
   return DS_LAUNCHED("ssim_bwd");
+}
+int dsgan_avgpool2_fwd2(const float* x1, float* y1, const float* x2, float* y2, int NC, int H, int W, void* stream) {
+  const long long total = (long long)NC * (H / 2 + (H & 1)) * (W / 2 + (W & 1));
+  k_avgpool2_fwd_pair<<<grid_for(2 * total, 256), 256, 0, (cudaStream_t)stream>>>(x1, y1, x2, y2, H, W, total);
+  return DS_LAUNCHED("avgpool2_fwd");
 }
 int dsgan_avgpool2_fwd(const float* x, float* y, int NC, int H, int W, void* stream) {
   const long long total = (long long)NC * (H / 2 + (H & 1)) * (W / 2 + (W & 1));

@@ -117,8 +117,7 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
         sizes.append((h - 10) * (w - 10))
         if lv < levels - 1:
             nx, ny = ws["px"][lv], ws["py"][lv]
-            L_.avgpool2_fwd(xs[lv].data_ptr(), nx.data_ptr(), NC, h, w, ctx.stream)
-            L_.avgpool2_fwd(ys[lv].data_ptr(), ny.data_ptr(), NC, h, w, ctx.stream)
+            L_.avgpool2_fwd2(xs[lv].data_ptr(), nx.data_ptr(), ys[lv].data_ptr(), ny.data_ptr(), NC, h, w, ctx.stream)
             xs.append(nx)
             ys.append(ny)
     coef = ws["coef"]
@@ -131,15 +130,13 @@ def ssim_value_and_grad(ctx: Ctx, X: torch.Tensor, Y: torch.Tensor, slot: int, o
                         coef.data_ptr() if want else None, ctx.stream)
     if not want:
         return
-    # backward: coarsest level first, each level's dY folded into the next finer one through avg_pool's adjoint
+    # backward: coarsest level first; each level adds the avg_pool adjoint of the next coarser level's dY on the fly
     g_next = None
     for lv in reversed(range(levels)):
         h, w = xs[lv].shape[-2:]
         g = dY if lv == 0 else ws["g"][lv - 1]
-        L_.ssim_bwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, coef[lv].data_ptr(), ws["mom"][lv].data_ptr(), g.data_ptr(),
-                    1 if lv == 0 else 0, ctx.stream)
-        if g_next is not None:
-            L_.avgpool2_bwd(g_next.data_ptr(), g.data_ptr(), NC, h, w, 1, ctx.stream)
+        L_.ssim_bwd(xs[lv].data_ptr(), ys[lv].data_ptr(), NC, h, w, C1, C2, coef[lv].data_ptr(), ws["mom"][lv].data_ptr(),
+                    g.data_ptr(), 1 if lv == 0 else 0, g_next.data_ptr() if g_next is not None else None, ctx.stream)
         g_next = g
 
 

@@ -270,11 +270,13 @@ int dsgan_ssim_fwd(const float* X, const float* Y, int NC, int H, int W, float C
                    void* stream);
 /* dY (=|+=) coef[nc,0] * d sum(ssim_map)/dY + coef[nc,1] * d sum(cs_map)/dY  (gradient w.r.t. the second argument only, as
  * the training call needs it, pix2pix_model.py:193-195).  moments = the buffer dsgan_ssim_fwd filled for the same X, Y, or
- * NULL (the moments are then recomputed on a halo: slower). */
+ * NULL (the moments are then recomputed on a halo: slower).  gnext (optional, needs moments): gradient of the next coarser
+ * ms-ssim level [NC, H/2 + H%2, W/2 + W%2]; its avg_pool adjoint (+ gnext/4) is added on the fly (MS_SSIM.py:214-216). */
 int dsgan_ssim_bwd(const float* X, const float* Y, int NC, int H, int W, float C1, float C2, const float* coef,
-                   const float* moments, float* dY, int accumulate, void* stream);
+                   const float* moments, float* dY, int accumulate, const float* gnext, void* stream);
 /* F.avg_pool2d(k=2) on NCHW fp32 planes (MS_SSIM.py:214-216) and its backward (dx += dy/4). */
 int dsgan_avgpool2_fwd(const float* x, float* y, int NC, int H, int W, void* stream);
+int dsgan_avgpool2_fwd2(const float* x1, float* y1, const float* x2, float* y2, int NC, int H, int W, void* stream);
 int dsgan_avgpool2_bwd(const float* dy, float* dx, int NC, int H, int W, int accumulate, void* stream);
 /* ms_ssim combine (MS_SSIM.py:218-225): sums [L,NC,2], sizes[L] = map pixel count, weights[L].
  * val[0] += out_scale * mean_nc prod_l relu(v_l)^w_l ; coef [L,NC,2] = grad_scale * d val / d sums. */

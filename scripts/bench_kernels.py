@@ -121,6 +121,17 @@ def main():
                  note="algorithmic bytes = 5*N*C*H*W*4 (SURVEY 8d); CUDA-graph replay of the whole call (value + dY)")
             emit(out, name + " fwd 64x3x256x256 fp32", timeit(graphed(fwd)), bytes_=2 * nbytes)
             emit(out, name + " fwd+bwd, eager host launches", timeit(fwd_bwd), bytes_=5 * nbytes)
+        # the two level-0 kernels on their own (ABI calls)
+        L, st = ctx.L, ctx.stream
+        NC, Hh, Ww = 64 * 3, 256, 256
+        sums = torch.zeros(NC, 2, device="cuda")
+        coef = torch.full((NC, 2), 1e-5, device="cuda")
+        mom = torch.empty(5, NC, Hh - 10, Ww - 10, device="cuda")
+        dY = torch.zeros_like(Y)
+        emit(out, "ssim_fwd kernel level 0 (no moments)", timeit(lambda: L.ssim_fwd(X.data_ptr(), Y.data_ptr(), NC, Hh, Ww, 1e-4, 9e-4, sums.data_ptr(), None, st)), bytes_=2 * nbytes)
+        emit(out, "ssim_fwd kernel level 0 (+ moments stored)", timeit(lambda: L.ssim_fwd(X.data_ptr(), Y.data_ptr(), NC, Hh, Ww, 1e-4, 9e-4, sums.data_ptr(), mom.data_ptr(), st)), bytes_=2 * nbytes)
+        emit(out, "ssim_bwd kernel level 0 (from moments)", timeit(lambda: L.ssim_bwd(X.data_ptr(), Y.data_ptr(), NC, Hh, Ww, 1e-4, 9e-4, coef.data_ptr(), mom.data_ptr(), dY.data_ptr(), 0, None, st)), bytes_=3 * nbytes)
+        emit(out, "ssim_bwd kernel level 0 (tiled, moments recomputed)", timeit(lambda: L.ssim_bwd(X.data_ptr(), Y.data_ptr(), NC, Hh, Ww, 1e-4, 9e-4, coef.data_ptr(), None, dY.data_ptr(), 0, None, st)), bytes_=3 * nbytes)
 
     # ---- InstanceNorm family on the uc4 / u4 tensor: 16 x 256 x 256 x 128 bf16 ---------------------------------
     if want("inorm"):
