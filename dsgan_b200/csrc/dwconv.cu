@@ -1,7 +1,9 @@
 // Depthwise k x k convolution (k = 3,5,7,9; stride 1; pad k/2) — CUDA-core, HBM/L2-bound.
 // Reference op sites: Block.dwconv (MixConvNeXtML.py:220) and MidMLKA.X3/X5/X7/X9 (:94-97).
 #include "common.cuh"
+#include "dwconv_mma.cuh"
 #include "../../include/dsgan_b200.h"
+#include <stdlib.h>
 using namespace dsgan;
 
 namespace {
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(256) k_dwconv_v8(const bf16* __restrict__ x, i
   constexpr int P = K / 2;
   const int c_base = blockIdx.y * VEC_CB;
   const int cb = min(VEC_CB, C - c_base);
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < K * K * cb; i += 256) {
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < K * K * cb; i += blockDim.x * blockDim.y) {
     const int tap = i / cb, c = i % cb;
     sw[tap][c] = __ldg(w + (size_t)(c_base + c) * K * K + (flip ? (K * K - 1 - tap) : tap));
   }
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v8(const bf16* __restrict_
   const int ky = blockIdx.z;
   const int c_base = blockIdx.y * VEC_CB;
   const int cb = min(VEC_CB, C - c_base);
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K + 1) * VEC_CB; i += 256) (&sacc[0][0])[i] = 0.f;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K + 1) * VEC_CB; i += blockDim.x * blockDim.y) (&sacc[0][0])[i] = 0.f;
   __syncthreads();
   const int cg = threadIdx.x;
   const bool active = cg * 8 < cb;
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v8(const bf16* __restrict_
     }
   }
   __syncthreads();
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K + 1) * cb; i += 256) {
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K + 1) * cb; i += blockDim.x * blockDim.y) {
     const int kx = i / cb, c = i % cb;
     if (kx < K) atomicAdd(dw + (size_t)(c_base + c) * K * K + ky * K + kx, sacc[kx][c]);
     else if (db && ky == 0) atomicAdd(db + c_base + c, sacc[K][c]);
@@ -312,7 +314,7 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
   constexpr int P = K / 2;
   const int c_base = blockIdx.y * CB;
   const int cb = min(CB, C - c_base);
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K * K + 1) * CB; i += 256) (&sacc[0][0])[i] = 0.f;
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K * K + 1) * CB; i += blockDim.x * blockDim.y) (&sacc[0][0])[i] = 0.f;
   __syncthreads();
   const int cp = threadIdx.x;
   const bool active = cp * 2 < cb;
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(256) k_dwconv_wgrad_v2(const bf16* __restrict_
     atomicAdd(&sacc[K * K][cp * 2 + 1], accb[1]);
   }
   __syncthreads();
-  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K * K + 1) * cb; i += 256) {
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < (K * K + 1) * cb; i += blockDim.x * blockDim.y) {
     const int t = i / cb, c = i % cb;
     if (t < K * K) atomicAdd(dw + (size_t)(c_base + c) * K * K + t, sacc[t][c]);
     else if (db) atomicAdd(db + c_base + c, sacc[K * K][c]);
@@ -613,6 +615,11 @@ inline bool vec_ok(const void* a, int lda, const void* b, int ldb, int C) {
 inline bool small_ok(const void* a, int lda, const void* b, int ldb, int C) {
   return C < 8 && lda % 8 == 0 && ldb % 8 == 0 && lda >= 8 && ldb >= 8 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0);
 }
+// DSGAN_DW_MMA=0 keeps the CUDA-core kernels (A/B measurements and the kernel tests that compare the two paths)
+inline bool dw_mma_enabled() {
+  const char* e = getenv("DSGAN_DW_MMA");
+  return !(e && e[0] == '0');
+}
 }  // namespace
 
 extern "C" {
@@ -620,6 +627,10 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
                      int H, int W, int C, int k, int flip, int accumulate, void* stream) {
   const long long total = (long long)N * H * W * C;
   cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DT_BF16 && dw_mma_enabled()) {
+    int rc = 0;
+    if (dwm::fwd_try((const bf16*)x, ld_x, w, bias, (bf16*)y, ld_y, N, H, W, C, k, flip, accumulate, s, &rc)) return rc;
+  }
   if (dtype == DT_BF16 && ((vec_ok(x, ld_x, y, ld_y, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) ||
                            small_ok(x, ld_x, y, ld_y, C))) {
     const bf16* xp = (const bf16*)x; bf16* yp = (bf16*)y;
@@ -664,6 +675,10 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
 int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float* dw, float* db, int dtype, int N,
                        int H, int W, int C, int k, void* stream) {
   const long long npix = (long long)N * H * W;
+  if (dtype == DT_BF16 && dw_mma_enabled()) {
+    int rc = 0;
+    if (dwm::wgrad_try((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, dw, db, N, H, W, C, k, (cudaStream_t)stream, &rc)) return rc;
+  }
   if (dtype == DT_BF16 && ((vec_ok(x, ld_x, dy, ld_dy, C) && (C >= 64 || C == 32 || C == 16 || C == 8)) ||
                            small_ok(x, ld_x, dy, ld_dy, C))) {
     const bf16* xp = (const bf16*)x; const bf16* gp = (const bf16*)dy;

@@ -147,15 +147,25 @@ def main():
         emit(out, "inorm_apply+GELU", timeit(lambda: L.inorm_apply(x.ptr, 128, stats.data_ptr(), None, 0, y.ptr, 128, 1, 16, HW, 128, 3, s)), bytes_=2 * nb)
         emit(out, "inorm_bwd_stats (GELU)", timeit(lambda: L.inorm_bwd_stats(x.ptr, 128, stats.data_ptr(), None, 0, dy.ptr, 128, 1, 16, HW, 128, 3, bst.data_ptr(), s)), bytes_=2 * nb)
         emit(out, "inorm_bwd_apply (GELU)", timeit(lambda: L.inorm_bwd_apply(x.ptr, 128, stats.data_ptr(), None, 0, dy.ptr, 128, bst.data_ptr(), dx.ptr, 128, 0, None, 0, 0, 1, 16, HW, 128, 3, None, None, s)), bytes_=3 * nb)
-        # ---- depthwise 7x7 on the same tensor
-        w = torch.randn(128, 1, 7, 7, device="cuda") * 0.1
-        b = torch.zeros(128, device="cuda")
-        dw, db = torch.zeros_like(w), torch.zeros_like(b)
-        emit(out, "dwconv7 fwd 16x256x256x128 bf16", timeit(lambda: L.dwconv_fwd(x.ptr, 128, w.data_ptr(), b.data_ptr(), y.ptr, 128, 1, 16, 256, 256, 128, 7, 0, 0, s)), bytes_=2 * nb)
-        emit(out, "dwconv7 dgrad (flip, overwrite)", timeit(lambda: L.dwconv_fwd(dy.ptr, 128, w.data_ptr(), None, dx.ptr, 128, 1, 16, 256, 256, 128, 7, 1, 0, s)), bytes_=2 * nb)
-        emit(out, "dwconv7 dgrad (flip, accumulate)", timeit(lambda: L.dwconv_fwd(dy.ptr, 128, w.data_ptr(), None, dx.ptr, 128, 1, 16, 256, 256, 128, 7, 1, 1, s)), bytes_=3 * nb)
-        emit(out, "dwconv7 wgrad", timeit(lambda: L.dwconv_wgrad(x.ptr, 128, dy.ptr, 128, dw.data_ptr(), db.data_ptr(), 1, 16, 256, 256, 128, 7, s)), bytes_=2 * nb)
         del x, y, dy, dx
+
+    # ---- depthwise convolutions at the Block shapes (bf16 NHWC) -----------------------------------------------
+    if want("dwconv"):
+        L, s = ctx.L, ctx.stream
+        for (Nn, Hh, Cc, kk) in ((16, 256, 128, 7), (16, 128, 256, 7), (16, 64, 512, 7), (16, 128, 32, 9)):
+            x, y, dy, dx = (ctx.new(Nn, Hh, Hh, Cc) for _ in range(4))
+            x.t.copy_(torch.randn(x.t.shape, device="cuda", generator=g))
+            dy.t.copy_(torch.randn(dy.t.shape, device="cuda", generator=g))
+            nb = x.t.numel() * 2
+            w = torch.randn(Cc, 1, kk, kk, device="cuda") * 0.1
+            b = torch.zeros(Cc, device="cuda")
+            dw, db = torch.zeros_like(w), torch.zeros_like(b)
+            tag = "dwconv%d %dx%dx%dx%d bf16 " % (kk, Nn, Hh, Hh, Cc)
+            emit(out, tag + "fwd", timeit(lambda: L.dwconv_fwd(x.ptr, Cc, w.data_ptr(), b.data_ptr(), y.ptr, Cc, 1, Nn, Hh, Hh, Cc, kk, 0, 0, s)), bytes_=2 * nb)
+            emit(out, tag + "dgrad (flip, overwrite)", timeit(lambda: L.dwconv_fwd(dy.ptr, Cc, w.data_ptr(), None, dx.ptr, Cc, 1, Nn, Hh, Hh, Cc, kk, 1, 0, s)), bytes_=2 * nb)
+            emit(out, tag + "dgrad (flip, accumulate)", timeit(lambda: L.dwconv_fwd(dy.ptr, Cc, w.data_ptr(), None, dx.ptr, Cc, 1, Nn, Hh, Hh, Cc, kk, 1, 1, s)), bytes_=3 * nb)
+            emit(out, tag + "wgrad", timeit(lambda: L.dwconv_wgrad(x.ptr, Cc, dy.ptr, Cc, dw.data_ptr(), db.data_ptr(), 1, Nn, Hh, Hh, Cc, kk, s)), bytes_=2 * nb)
+            del x, y, dy, dx
 
     # ---- tcgen05 pointwise GEMMs at the Block shapes (N=16) ---------------------------------------------------
     if want("gemm"):

@@ -133,6 +133,48 @@ def test_dwconv(prec, k, C):
     assert rel(P["b"].grad.cpu(), br.grad) < tol
 
 
+def _dwconv_run(x, w, b, dy, k, twice):
+    """forward + backward of the bf16 depthwise conv through the engine; twice: x feeds two convs (gradient fan-in)"""
+    ctx = ctx_for("bf16")
+    P = make_params({"w": w, "b": b})
+    xv = to_var(ctx, x)
+    yv = E.dwconv(ctx, xv, P["w"], P["b"], k)
+    if twice:
+        y2 = E.dwconv(ctx, xv, P["w"], P["b"], k)
+        set_grad(ctx, y2, dy)
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    return var_data(yv), var_grad(xv), P["w"].grad.cpu().clone(), P["b"].grad.cpu().clone()
+
+
+@pytest.mark.parametrize("cfg", [
+    # (N, C, H, W, k): shapes taken by the tensor-core path (C >= 16, C % 8 == 0, H >= 16, W >= 32), ragged tiles included
+    (2, 16, 32, 64, 7), (1, 24, 40, 72, 7), (2, 64, 64, 32, 3), (1, 32, 16, 32, 9), (1, 128, 48, 96, 5), (2, 32, 33, 47, 7),
+    (1, 40, 70, 130, 9),
+])
+@pytest.mark.parametrize("twice", [False, True])
+def test_dwconv_mma(cfg, twice, monkeypatch):
+    """mma.sync depthwise path (dwconv_mma.cu) against torch fp32 AND against the CUDA-core kernels it replaces"""
+    N, C, H, W, k = cfg
+    x = q(torch.randn(N, C, H, W, generator=_g(1)), "bf16")
+    w = torch.randn(C, 1, k, k, generator=_g(2)) / k
+    b = torch.randn(C, generator=_g(3)) * 0.1
+    dy = q(torch.randn(N, C, H, W, generator=_g(4)), "bf16")
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, padding=k // 2, groups=C)
+    yr.backward(dy * (2 if twice else 1))
+    monkeypatch.setenv("DSGAN_DW_MMA", "1")
+    y1, dx1, dw1, db1 = _dwconv_run(x, w, b, dy, k, twice)
+    monkeypatch.setenv("DSGAN_DW_MMA", "0")
+    y0, dx0, dw0, db0 = _dwconv_run(x, w, b, dy, k, twice)
+    tol = TOL["bf16"]
+    assert rel(y1, yr.detach()) < tol and rel(dx1, xr.grad) < tol
+    assert rel(dw1, wr.grad) < 1e-3 and rel(db1, br.grad) < 1e-3     # exact bf16 products, fp32 sums
+    # same arithmetic as the fp32-weight CUDA-core kernels up to the summation order (hi + lo weight split)
+    assert rel(y1, y0) < 2e-3 and rel(dx1, dx0) < 3e-3
+    assert rel(dw1, dw0) < 1e-4 and rel(db1, db0) < 1e-4
+
+
 @pytest.mark.parametrize("prec", PREC)
 @pytest.mark.parametrize("act", [None, "gelu", "leaky"])
 @pytest.mark.parametrize("with_res", [False, True])
