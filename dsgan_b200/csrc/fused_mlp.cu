@@ -381,12 +381,12 @@ struct BwdCfg {
   static constexpr int NGS = 4;                         // G slab buffers: the TMA store / column sums of chunk j may lag
   static constexpr int GS_OFF = DY_OFF + KBO * BOX;     //   behind the epilogue by up to three chunks
   static constexpr int RING_OFF = GS_OFF + NGS * BOX;
-  static constexpr int FIXED = 1024 + 1024 + 8 * HID;
+  static constexpr int FIXED = 1024 + 1024 + 1024 + 8 * HID;
   static constexpr int RING_MAX = (SMEM_LIMIT - RING_OFF - FIXED) / BOX8;
   static constexpr int RING = RING_MAX > 16 ? 16 : RING_MAX;
   static constexpr int BAR_OFF = RING_OFF + RING * BOX8;
   static constexpr int BIAS_OFF = BAR_OFF + 1024;
-  static constexpr int TOTAL = BIAS_OFF + 8 * HID + 1024;   // b1 + the CTA's partial pwconv1 bias gradient
+  static constexpr int TOTAL = BIAS_OFF + 8 * HID + 1024 + 1024;   // b1 + the CTA's partial bias gradients (pwconv1: HID, pwconv2: <= 256)
   static_assert(RING >= 4, "weight ring too small");
   static_assert(NCH % NGS == 0, "hidden must be a multiple of 256");
   static_assert(256 + CIN <= 512, "tensor memory budget");
@@ -399,6 +399,7 @@ struct BwdParams {
   void* dT;
   int ld_dt;
   float* db1;
+  float* db2;   // pwconv2 bias gradient = column sums of dY (may be null)
   void* A;      // bf16 [M, HID]: written straight from the epilogue registers (one 32-byte store per lane and chunk)
 };
 
@@ -423,6 +424,7 @@ k_mlp_bwd(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dt_empty + 1);
   float* sb1 = reinterpret_cast<float*>(smem + C::BIAS_OFF);
   float* sdb = sb1 + C::HID;
+  float* sdb2 = sdb + C::HID;         // [NOUT]
 
   const int wr = threadIdx.x >> 5, lane = threadIdx.x & 31;      // physical warp; helper roles on the highest ids (see forward)
   const int warp = (wr + 4) % (BWD_THREADS / 32);                // logical: 0 producer, 1 MMA, 2 store, 3 column sums, 4.. epilogue
@@ -431,7 +433,7 @@ k_mlp_bwd(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUten
     tma_prefetch_desc(&tmT); tma_prefetch_desc(&tmDY); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmG);
     for (int i = 0; i < C::RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(td_full, 1); mbar_init(td_empty, 1);
+    mbar_init(td_full, 1); mbar_init(td_empty, 2);   // released by the MMA issuer's commit and by the column-sum warp
     for (int i = 0; i < 2; ++i) { mbar_init(&hd_full[i], 1); mbar_init(&hd_empty[i], EPI_WARPS); }
     for (int i = 0; i < C::NGS; ++i) {
       mbar_init(&gs_full[i], EPI_WARPS); mbar_init(&gs_empty[i], 3);   // DT(j) commit + store warp + column-sum warp
@@ -441,6 +443,7 @@ k_mlp_bwd(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUten
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   for (int i = threadIdx.x; i < C::HID; i += BWD_THREADS) { sb1[i] = __ldg(p.b1 + i); sdb[i] = 0.f; }
+  for (int i = threadIdx.x; i < NOUT; i += BWD_THREADS) sdb2[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -570,45 +573,58 @@ k_mlp_bwd(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUten
     // ================= column-sum warp: pwconv1 bias gradient = column sums of G =================
     // lane = (16-byte chunk c = 8 columns, row offset ro): one LDS.128 per 4 rows, conflict-free under the 128-byte swizzle
     const int c = lane & 7, ro = lane >> 3;
+    // column sums of one [128 x 64] bf16 slab (128-byte swizzled rows) added to dst[64]
+    auto slab_sums = [&](const uint8_t* gsl, float* dst) {
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < BM / 4; ++i) {
+        const int rr = i * 4 + ro;
+        const uint4 w4 = *reinterpret_cast<const uint4*>(gsl + rr * 128 + ((c ^ (rr & 7)) << 4));
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[2 * e] += __uint_as_float(w[e] << 16);
+          v[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
+        v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
+      }
+      if (ro == 0) {
+        float* d = dst + c * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += v[e];
+      }
+      __syncwarp();
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      // pwconv2 bias gradient: the dY tile is resident for the whole tile; rows past M arrive as zeros
+      mbar_wait(td_full, (uint32_t)(it & 1));
+      if (p.db2) {
+#pragma unroll 1
+        for (int kb = 0; kb < C::KBO; ++kb) slab_sums(smem + C::DY_OFF + kb * BOX, sdb2 + kb * 64);
+      }
+      if (lane == 0) mbar_arrive(td_empty);
 #pragma unroll 1
       for (int j = 0; j < C::NCH; ++j) {
         const int gb = j & (C::NGS - 1);
         const uint32_t ug = (uint32_t)(it * (C::NCH / C::NGS) + j / C::NGS);
         mbar_wait(&gs_full[gb], ug & 1);
-        const uint8_t* gsl = smem + C::GS_OFF + gb * BOX;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < BM / 4; ++i) {
-          const int rr = i * 4 + ro;
-          const uint4 w4 = *reinterpret_cast<const uint4*>(gsl + rr * 128 + ((c ^ (rr & 7)) << 4));
-          const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[2 * e] += __uint_as_float(w[e] << 16);
-            v[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          v[e] += __shfl_xor_sync(0xffffffffu, v[e], 8);
-          v[e] += __shfl_xor_sync(0xffffffffu, v[e], 16);
-        }
-        if (ro == 0) {
-          float* d = sdb + j * 64 + c * 8;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d[e] += v[e];
-        }
-        __syncwarp();
+        slab_sums(smem + C::GS_OFF + gb * BOX, sdb + j * 64);
         if (lane == 0) mbar_arrive(&gs_empty[gb]);
       }
     }
+    __syncwarp();
     if (p.db1) {
-      __syncwarp();
       for (int i = lane; i < C::HID; i += 32) atomicAdd(p.db1 + i, sdb[i]);
+    }
+    if (p.db2) {
+      for (int i = lane; i < NOUT; i += 32) atomicAdd(p.db2 + i, sdb2[i]);
     }
   } else {
     // ================= epilogue warps: 32 rows x 16 columns of every chunk per warp, in two 8-column stages whose
@@ -710,7 +726,7 @@ k_mlp_bwd(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUten
 
 template <int CIN, int NOUT>
 int launch_bwd(const void* T, int ld_t, const void* dY, int ld_dy, long long M, const void* W1, const float* b1,
-               const void* W2, void* dT, int ld_dt, void* G, void* A, float* db1, cudaStream_t s) {
+               const void* W2, void* dT, int ld_dt, void* G, void* A, float* db1, float* db2, cudaStream_t s) {
   using C = BwdCfg<CIN, NOUT>;
   static bool attr = false;
   if (!attr) {
@@ -726,7 +742,7 @@ int launch_bwd(const void* T, int ld_t, const void* dY, int ld_dy, long long M, 
   if (get_map_2d(&tG, G, C::HID, (uint64_t)M, C::HID, 64, 128)) return 1;
   BwdParams p;
   p.M = (int)M; p.m_tiles = (int)((M + BM - 1) / BM);
-  p.b1 = b1; p.dT = dT; p.ld_dt = ld_dt; p.db1 = db1; p.A = A;
+  p.b1 = b1; p.dT = dT; p.ld_dt = ld_dt; p.db1 = db1; p.db2 = db2; p.A = A;
   const int grid = p.m_tiles < num_sms() ? p.m_tiles : num_sms();
   k_mlp_bwd<CIN, NOUT><<<grid, BWD_THREADS, C::TOTAL, s>>>(tT, tDY, tW1, tW2, tG, p);
   return DS_LAUNCHED("fused_mlp_bwd");
@@ -761,7 +777,7 @@ int dsgan_fused_mlp_fwd(const void* T, int ld_t, const void* X, int ld_x, long l
 }
 
 int dsgan_fused_mlp_bwd(const void* T, int ld_t, const void* dY, int ld_dy, long long M, int Cin, int Nout, const void* W1,
-                        const float* b1, const void* W2, void* dT, int ld_dt, void* G, void* A, float* db1,
+                        const float* b1, const void* W2, void* dT, int ld_dt, void* G, void* A, float* db1, float* db2,
                         void* stream) {
   DS_REQUIRE(dsgan_fused_mlp_supported(Cin, Nout), "fused_mlp_bwd: unsupported channels Cin=%d Nout=%d", Cin, Nout);
   DS_REQUIRE(M >= 1 && ld_t % 8 == 0 && ld_dy % 8 == 0 && ld_dt % 16 == 0, "fused_mlp_bwd: bad pitches");
@@ -770,7 +786,7 @@ int dsgan_fused_mlp_bwd(const void* T, int ld_t, const void* dY, int ld_dy, long
              "fused_mlp_bwd: unaligned pointer");
   DS_REQUIRE(b1 && G && A && dT, "fused_mlp_bwd: null argument");
   cudaStream_t s = (cudaStream_t)stream;
-#define MLP_CASE(CI, NO) if (Cin == CI && Nout == NO) return launch_bwd<CI, NO>(T, ld_t, dY, ld_dy, M, W1, b1, W2, dT, ld_dt, G, A, db1, s);
+#define MLP_CASE(CI, NO) if (Cin == CI && Nout == NO) return launch_bwd<CI, NO>(T, ld_t, dY, ld_dy, M, W1, b1, W2, dT, ld_dt, G, A, db1, db2, s);
   MLP_CASE(64, 64) MLP_CASE(64, 128) MLP_CASE(64, 256)
   MLP_CASE(128, 64) MLP_CASE(128, 128) MLP_CASE(128, 256)
   MLP_CASE(256, 64) MLP_CASE(256, 128)

@@ -606,11 +606,10 @@ def block_mlp(ctx: Ctx, x: Var, t_fn, w1: Param, b1: Param, w2: Param, b2: Param
             L.profiler.pending_flops = 2.0 * M * (H4 * Nout + H4 * Cin)
             L.profiler.label = "M%d %d->%d->%d" % (M, Cin, H4, Nout)
         L.fused_mlp_bwd(t.ptr, t.ld, gi[0], gi[1], M, Cin, Nout, w1.bf16_ptr, b1.ptr, w2.bf16_ptr, gp, gld, G.data_ptr(),
-                        A.data_ptr(), b1.gptr if train_w else None, ctx.stream)
+                        A.data_ptr(), b1.gptr if train_w else None, b2.gptr if train_w else None, ctx.stream)
         if train_w:
             ctx.tc_wgrad((G.data_ptr(), H4), (t.ptr, t.ld), M, H4, Cin, w1.gptr)
             ctx.tc_wgrad(gi, (A.data_ptr(), H4), M, Nout, H4, w2.gptr)
-            ctx.colsum(gi, M, Nout, b2.gptr)
     ctx.record(bwd_mlp)
     return y
 

@@ -124,9 +124,10 @@ int dsgan_fused_mlp_fwd(const void* T, int ld_t, const void* X, int ld_x, long l
 /* Backward of the MLP part (shortcut excluded) with the hidden recomputed:
  *   Hpre = T.W1^T + b1;  A = GELU(Hpre);  G = (dY.W2) * GELU'(Hpre);  dT = G.W1      (MixConvNeXtML.py:236-240 backward)
  * dT: bf16 [M,Cin] (overwritten).  G, A: bf16 [M,4Cin] workspaces, fully written - the operands of the two weight-gradient
- * GEMMs (dW1 = G^T.T, dW2 = dY^T.A via dsgan_tc_wgrad).  db1 (fp32 [4Cin], +=, optional) = column sums of G. */
+ * GEMMs (dW1 = G^T.T, dW2 = dY^T.A via dsgan_tc_wgrad).  db1 (fp32 [4Cin], +=, optional) = column sums of G;
+ * db2 (fp32 [Nout], +=, optional) = column sums of dY, taken from the resident dY tile (no separate pass over dY). */
 int dsgan_fused_mlp_bwd(const void* T, int ld_t, const void* dY, int ld_dy, long long M, int Cin, int Nout, const void* W1,
-                        const float* b1, const void* W2, void* dT, int ld_dt, void* G, void* A, float* db1,
+                        const float* b1, const void* W2, void* dT, int ld_dt, void* G, void* A, float* db1, float* db2,
                         void* stream);
 /* dst (bf16) = src (fp32), n elements: refresh of the packed GEMM operands after an optimizer step. */
 int dsgan_pack_bf16(const float* src, void* dst, long long n, void* stream);

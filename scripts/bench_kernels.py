@@ -252,7 +252,7 @@ def main():
             emit(out, "fused_mlp_fwd %s M%d %d->%d->%d (+shortcut)" % (name, M, cin, hid, nout), ms, flops=fl_f,
                  hbm_bytes=2 * M * (2 * cin + nout), hbm_bound_ms=round(2 * M * (2 * cin + nout) / PEAK["hbm_gbs"] / 1e6, 4))
             ms = timeit(lambda: L.fused_mlp_bwd(T.data_ptr(), cin, dY.data_ptr(), nout, M, cin, nout, W1.data_ptr(), b1.data_ptr(),
-                                                W2.data_ptr(), dT.data_ptr(), cin, G.data_ptr(), A.data_ptr(), db1.data_ptr(), st))
+                                                W2.data_ptr(), dT.data_ptr(), cin, G.data_ptr(), A.data_ptr(), db1.data_ptr(), None, st))
             nb = 2 * M * (2 * cin + nout + 2 * hid)
             emit(out, "fused_mlp_bwd %s M%d %d->%d->%d (dT, G, A, db1; hidden recomputed)" % (name, M, cin, hid, nout), ms,
                  flops=fl_b, hbm_bytes=nb, hbm_bound_ms=round(nb / PEAK["hbm_gbs"] / 1e6, 4),

@@ -102,7 +102,7 @@ def _ref_bwd(T, dY, W1, b1, W2):
 @pytest.mark.parametrize("cin,nout", SHAPES)
 @pytest.mark.parametrize("M", [128, 1000, 128 * 300 + 64])
 def test_fused_mlp_bwd(cin, nout, M):
-    """dT, G = dH * GELU'(Hpre), A = GELU(Hpre) and db1 = colsum(G) against torch autograd on the same bf16 operands."""
+    """dT, G = dH * GELU'(Hpre), A = GELU(Hpre), db1 = colsum(G) and db2 = colsum(dY) against torch autograd on the same bf16 operands."""
     L = lib()
     T, _X, W1, b1, W2, _b2, _Ws = _case(M, cin, nout, seed=7 + cin + nout + M)
     dY = _bf(torch.randn(M, nout, generator=_g(99 + M)) * 0.1)
@@ -112,10 +112,11 @@ def test_fused_mlp_bwd(cin, nout, M):
     G = torch.empty((M, hid), dtype=torch.bfloat16, device="cuda")
     A = torch.empty((M, hid), dtype=torch.bfloat16, device="cuda")
     db1 = torch.full((hid,), 0.5, dtype=torch.float32, device="cuda")
+    db2 = torch.full((nout,), 0.25, dtype=torch.float32, device="cuda")
     dT_, dY_, W1_, W2_, b1_ = _dev(T), _dev(dY), _dev(W1), _dev(W2), _dev(b1, torch.float32)
     s = torch.cuda.current_stream().cuda_stream
     L.fused_mlp_bwd(dT_.data_ptr(), cin, dY_.data_ptr(), nout, M, cin, nout, W1_.data_ptr(), b1_.data_ptr(), W2_.data_ptr(),
-                    dTd.data_ptr(), 2 * cin, G.data_ptr(), A.data_ptr(), db1.data_ptr(), s)
+                    dTd.data_ptr(), 2 * cin, G.data_ptr(), A.data_ptr(), db1.data_ptr(), db2.data_ptr(), s)
     torch.cuda.synchronize()
     assert torch.all(dTd[:, cin:].float() == 3.0), "wrote outside the dT slice"
     assert rel(A.float().cpu(), want_A) < 4e-3
@@ -125,3 +126,5 @@ def test_fused_mlp_bwd(cin, nout, M):
     want_db = G.float().cpu().sum(0)                              # the kernel sums its own (rounded) G
     assert float((got_db - want_db).abs().max()) <= 2e-3 * float(want_db.abs().max()) + 1e-4
     assert rel(got_db, want_G.sum(0)) < 2e-2
+    want_db2 = dY.float().sum(0)                                   # pwconv2 bias gradient: exact bf16 inputs, fp32 sums
+    assert float(((db2.cpu() - 0.25) - want_db2).abs().max()) <= 1e-4 * float(want_db2.abs().max()) + 1e-4
