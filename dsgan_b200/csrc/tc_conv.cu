@@ -15,6 +15,7 @@
 #include "tc_common.cuh"
 #include "../../include/dsgan_b200.h"
 #include "sc_conv.cuh"
+#include "nm_conv.cuh"
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -694,7 +695,8 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
     return d->co_pad == 64 ? launch_halo<64>(ta, tb, p, (cudaStream_t)stream) : launch_halo<32>(ta, tb, p, (cudaStream_t)stream);
   }
   {
-    int rc = 0;   // 1/3/6/12-channel layers: CUDA-core direct convolution (sc_conv.cu), same contract
+    int rc = 0;   // 1/3/6/12-channel layers: (tap, padded channel) implicit GEMM on mma.sync (nm_conv.cu), else the CUDA-core
+    if (nm::conv_try(d, in, w_slabs, bias, out, pre_out, aux, stream, &rc)) return rc;   // direct convolution (sc_conv.cu)
     if (sc::conv_try(d, in, w_slabs, bias, out, pre_out, aux, stream, &rc)) return rc;
   }
   const int BN = d->Co >= 256 ? 256 : (d->Co >= 128 ? 128 : (d->Co >= 64 ? 64 : 32));
