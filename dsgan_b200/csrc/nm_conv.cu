@@ -178,6 +178,145 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the narrow layers:  dW[tap][m][n] += sum_px G[px][m] * X[px*xs + tap][n]  with one side of 1/3/6/12
+// channels.  M = the wide side's channels (m16 tiles), N = the narrow side padded to 8/16, K = grid positions: both operands
+// are NHWC tiles whose rows are pixels, read through ldmatrix.trans; the tap shift is a per-lane row address on the X tile.
+// CTA = 8 x 32 grid positions; warp = (m16 tile of the wide side, pixel group); accumulators persist over all tiles of the
+// CTA and are reduced once (shared, then one atomicAdd per weight and CTA).
+struct NmWgParams {
+  int N, Hg, Wg, Cg, ld_g, Hx, Wx, Cx, ld_x, xs, ntaps;
+  int dy[16], dx[16];
+  long long tap_off[16];
+  long long s_g, s_x;
+  int wide_is_g, mt_total, cgp, cxp, gpitch, xpitch;
+  int dy_min, dx_min, xrows, xcols;
+  int tiles_x, tiles_y, total_tiles, nbuf, gbytes, xbytes;
+  const bf16* G; const bf16* X; float* dW;
+};
+
+__device__ __forceinline__ void ldsm_x4_t(uint32_t a, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t a, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+
+template <int NTAPS, int NTn>
+__global__ void __launch_bounds__(THREADS, 2) k_nm_wgrad(const NmWgParams p) {
+  constexpr int CNP = 8 * NTn;
+  extern __shared__ __align__(128) unsigned char dsm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int cwp = 16 * p.mt_total;
+  float* sdw = reinterpret_cast<float*>(dsm);                        // [NTAPS][cwp][CNP]
+  int* toff = reinterpret_cast<int*>(sdw + NTAPS * cwp * CNP);
+  unsigned char* gbuf = reinterpret_cast<unsigned char*>(toff + 16);
+  unsigned char* xbuf = gbuf + p.nbuf * p.gbytes;
+  for (int i = tid; i < NTAPS * cwp * CNP; i += THREADS) sdw[i] = 0.f;
+  if (tid < NTAPS) toff[tid] = ((p.dy[tid] - p.dy_min) * p.xcols + (p.dx[tid] - p.dx_min)) * p.xpitch;
+  const uint32_t g_u = (uint32_t)__cvta_generic_to_shared(gbuf), x_u = (uint32_t)__cvta_generic_to_shared(xbuf);
+
+  auto prefetch = [&](int tile, int buf) {
+    const int img = tile / (p.tiles_x * p.tiles_y), ty = (tile / p.tiles_x) % p.tiles_y, tx = tile % p.tiles_x;
+    const int gy0 = ty * TH, gx0 = tx * TW;
+    const int cg8 = p.cgp / 8, cx8 = p.cxp / 8;
+    for (int i = tid; i < TH * TW * cg8; i += THREADS) {
+      const int h = i % cg8, px = (i / cg8) % TW, py = i / (cg8 * TW);
+      const int gy = gy0 + py, gx = gx0 + px;
+      const bool ok = gy < p.Hg && gx < p.Wg && h * 8 < p.ld_g;
+      const bf16* src = ok ? p.G + (((size_t)img * p.Hg + gy) * p.Wg + gx) * p.ld_g + h * 8 : p.G;
+      cp_async16_zfill(g_u + buf * p.gbytes + (py * TW + px) * p.gpitch + h * 16, src, ok);
+    }
+    const int iy0 = gy0 * p.xs + p.dy_min, ix0 = gx0 * p.xs + p.dx_min;
+    for (int i = tid; i < p.xrows * p.xcols * cx8; i += THREADS) {
+      const int h = i % cx8, pxl = (i / cx8) % p.xcols, pyl = i / (cx8 * p.xcols);
+      const int iy = iy0 + pyl, ix = ix0 + pxl;
+      const bool ok = iy >= 0 && iy < p.Hx && ix >= 0 && ix < p.Wx && h * 8 < p.ld_x;
+      const bf16* src = ok ? p.X + (((size_t)img * p.Hx + iy) * p.Wx + ix) * p.ld_x + h * 8 : p.X;
+      cp_async16_zfill(x_u + buf * p.xbytes + (pyl * p.xcols + pxl) * p.xpitch + h * 16, src, ok);
+    }
+    cp_async_commit();
+  };
+
+  float acc[NTAPS][NTn][4];
+#pragma unroll
+  for (int tp = 0; tp < NTAPS; ++tp)
+#pragma unroll
+    for (int nt = 0; nt < NTn; ++nt) acc[tp][nt][0] = acc[tp][nt][1] = acc[tp][nt][2] = acc[tp][nt][3] = 0.f;
+
+  const int mt = warp % p.mt_total, pg = warp / p.mt_total, npg = 8 / p.mt_total;
+  // A (wide side): matrices (k 0-7 | k 8-15) x (m 0-7 | m 8-15);  B (narrow side): k 0-7, k 8-15 for lanes 0..15
+  const int a_px = (lane & 7) + (lane >> 4) * 8, a_ch = ((lane >> 3) & 1) * 16 + mt * 32;
+  const int b_px = lane & 15;
+
+  if ((int)blockIdx.x < p.total_tiles && p.nbuf == 2) prefetch(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    int buf = 0;
+    if (p.nbuf == 2) {
+      buf = it & 1;
+      cp_async_wait_all();
+      __syncthreads();
+      if (tile + (int)gridDim.x < p.total_tiles) prefetch(tile + gridDim.x, buf ^ 1);
+    } else {
+      __syncthreads();           // previous tile consumed
+      prefetch(tile, 0);
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    const uint32_t gt = g_u + buf * p.gbytes, xt = x_u + buf * p.xbytes;
+#pragma unroll 1
+    for (int ks = pg; ks < 16; ks += npg) {
+      const int r = ks >> 1, c0 = (ks & 1) * 16;
+      if (p.wide_is_g) {
+        uint32_t a[4];
+        ldsm_x4_t(gt + (r * TW + c0 + a_px) * p.gpitch + a_ch, a[0], a[1], a[2], a[3]);
+        const uint32_t xb = xt + ((r * p.xs) * p.xcols + (c0 + b_px) * p.xs) * p.xpitch;
+#pragma unroll
+        for (int tp = 0; tp < NTAPS; ++tp) {
+#pragma unroll
+          for (int nt = 0; nt < NTn; ++nt) {
+            uint32_t b0, b1;
+            ldsm_x2_t(xb + toff[tp] + nt * 16, b0, b1);
+            mma16816(acc[tp][nt], a, b0, b1);
+          }
+        }
+      } else {
+        uint32_t b[NTn][2];
+#pragma unroll
+        for (int nt = 0; nt < NTn; ++nt) ldsm_x2_t(gt + (r * TW + c0 + b_px) * p.gpitch + nt * 16, b[nt][0], b[nt][1]);
+        const uint32_t xa = xt + ((r * p.xs) * p.xcols + (c0 + a_px) * p.xs) * p.xpitch + a_ch;
+#pragma unroll
+        for (int tp = 0; tp < NTAPS; ++tp) {
+          uint32_t a[4];
+          ldsm_x4_t(xa + toff[tp], a[0], a[1], a[2], a[3]);
+#pragma unroll
+          for (int nt = 0; nt < NTn; ++nt) mma16816(acc[tp][nt], a, b[nt][0], b[nt][1]);
+        }
+      }
+    }
+  }
+  // reduce: fragment element e of thread (g, t) is (m = mt*16 + g + 8*(e>>1), n = nt*8 + 2t + (e&1))
+  const int cw = p.wide_is_g ? p.Cg : p.Cx, cn = p.wide_is_g ? p.Cx : p.Cg;
+#pragma unroll
+  for (int tp = 0; tp < NTAPS; ++tp)
+#pragma unroll
+    for (int nt = 0; nt < NTn; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int m = mt * 16 + g + 8 * (e >> 1), n = nt * 8 + 2 * t + (e & 1);
+        if (m < cw && n < cn) atomicAdd(sdw + (tp * cwp + m) * CNP + n, acc[tp][nt][e]);
+      }
+  __syncthreads();
+  for (int i = tid; i < NTAPS * cwp * CNP; i += THREADS) {
+    const int n = i % CNP, m = (i / CNP) % cwp, tp = i / (CNP * cwp);
+    if (m >= cw || n >= cn) continue;
+    const long long off = p.tap_off[tp] + (p.wide_is_g ? m * p.s_g + n * p.s_x : n * p.s_g + m * p.s_x);
+    atomicAdd(p.dW + off, sdw[i]);
+  }
+}
+
 int sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -201,6 +340,21 @@ int launch(const NmParams& p, size_t smem, cudaStream_t s) {
   grid = (p.total_tiles + per - 1) / per;
   k_nm_conv<CP, NTN><<<grid, THREADS, smem, s>>>(p);
   return DS_LAUNCHED("nm_conv");
+}
+
+template <int NTAPS, int NTn>
+int launch_wg(const NmWgParams& p, size_t smem, cudaStream_t s) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaFuncSetAttribute(k_nm_wgrad<NTAPS, NTn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = smem;
+  }
+  int grid = (smem > 110 * 1024 ? 1 : 2) * sm_count();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  const int per = (p.total_tiles + grid - 1) / grid;
+  grid = (p.total_tiles + per - 1) / per;
+  k_nm_wgrad<NTAPS, NTn><<<grid, THREADS, smem, s>>>(p);
+  return DS_LAUNCHED("nm_wgrad");
 }
 }  // namespace
 
@@ -253,6 +407,57 @@ bool conv_try(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, 
 #define NM_CASE(CPV, NT) if (CP == CPV && NTN == NT) { *rc = launch<CPV, NT>(p, smem, s); return true; }
   NM_CASE(8, 2) NM_CASE(8, 4) NM_CASE(8, 8) NM_CASE(16, 2) NM_CASE(16, 4) NM_CASE(16, 8)
 #undef NM_CASE
+  return false;
+}
+
+bool wgrad_try(const dsgan_tc_wgrad_desc* d, const void* G, const void* X, float* dW, void* stream, int* rc) {
+  {
+    const char* e = getenv("DSGAN_NM_CONV");
+    if (e && e[0] == '0') return false;
+  }
+  auto narrow = [](int c) { return c == 1 || c == 3 || c == 6 || c == 12; };
+  const bool ng = narrow(d->Cg), nx = narrow(d->Cx);
+  if (!ng && !nx) return false;
+  const bool wide_is_g = nx && (!ng || d->Cg >= d->Cx);
+  const int cw = wide_is_g ? d->Cg : d->Cx, cn = wide_is_g ? d->Cx : d->Cg;
+  if (cw > 64 || (d->ntaps != 1 && d->ntaps != 9 && d->ntaps != 16) || (d->x_stride != 1 && d->x_stride != 2)) return false;
+  if (d->ld_g % 8 || d->ld_x % 8 || (uintptr_t)G % 16 || (uintptr_t)X % 16) return false;
+  NmWgParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Cg = d->Cg; p.ld_g = d->ld_g; p.Hx = d->Hx; p.Wx = d->Wx; p.Cx = d->Cx;
+  p.ld_x = d->ld_x; p.xs = d->x_stride; p.ntaps = d->ntaps;
+  int dy0 = 1 << 30, dy1 = -(1 << 30), dx0 = 1 << 30, dx1 = -(1 << 30);
+  for (int t = 0; t < d->ntaps; ++t) {
+    p.dy[t] = d->dy[t]; p.dx[t] = d->dx[t]; p.tap_off[t] = d->tap_off[t];
+    dy0 = d->dy[t] < dy0 ? d->dy[t] : dy0; dy1 = d->dy[t] > dy1 ? d->dy[t] : dy1;
+    dx0 = d->dx[t] < dx0 ? d->dx[t] : dx0; dx1 = d->dx[t] > dx1 ? d->dx[t] : dx1;
+  }
+  p.s_g = d->s_g; p.s_x = d->s_x; p.wide_is_g = wide_is_g ? 1 : 0;
+  const int mt = (cw + 15) / 16;
+  p.mt_total = mt == 3 ? 4 : mt;
+  const int NTn = cn > 8 ? 2 : 1;
+  const int cwp = 16 * p.mt_total, cnp = 8 * NTn;
+  p.cgp = wide_is_g ? cwp : cnp; p.cxp = wide_is_g ? cnp : cwp;
+  auto pitch = [](int cp) { const int b = cp * 2; return (b / 16) % 2 == 0 ? b + 16 : b; };   // odd number of 16-byte units
+  p.gpitch = pitch(p.cgp); p.xpitch = pitch(p.cxp);
+  p.dy_min = dy0; p.dx_min = dx0;
+  p.xrows = (TH - 1) * p.xs + (dy1 - dy0) + 1;
+  p.xcols = (TW - 1) * p.xs + (dx1 - dx0) + 1;
+  p.tiles_x = (d->Wg + TW - 1) / TW; p.tiles_y = (d->Hg + TH - 1) / TH;
+  const long long total = (long long)d->N * p.tiles_x * p.tiles_y;
+  if (total >= (1LL << 31)) return false;
+  p.total_tiles = (int)total;
+  p.gbytes = (TH * TW * p.gpitch + 127) & ~127;
+  p.xbytes = (p.xrows * p.xcols * p.xpitch + 127) & ~127;
+  const size_t fixed = (size_t)d->ntaps * cwp * cnp * 4 + 64;
+  p.nbuf = (fixed + 2 * (size_t)(p.gbytes + p.xbytes) <= 110 * 1024) ? 2 : 1;
+  const size_t smem = fixed + (size_t)p.nbuf * (p.gbytes + p.xbytes);
+  if (smem > 200 * 1024) return false;
+  p.G = (const bf16*)G; p.X = (const bf16*)X; p.dW = dW;
+  cudaStream_t s = (cudaStream_t)stream;
+#define NMW_CASE(NT, NN) if (d->ntaps == NT && NTn == NN) { *rc = launch_wg<NT, NN>(p, smem, s); return true; }
+  NMW_CASE(1, 1) NMW_CASE(1, 2) NMW_CASE(9, 1) NMW_CASE(9, 2) NMW_CASE(16, 1)   // (16 taps x 2 narrow tiles would need 128 accumulator registers: not built)
+#undef NMW_CASE
   return false;
 }
 

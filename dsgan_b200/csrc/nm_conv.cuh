@@ -6,5 +6,6 @@ namespace nm {
 // -> true if the shape was taken (then *rc holds the launch status); false: the caller tries the next backend
 bool conv_try(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, const float* bias, void* out, void* pre_out,
               const void* aux, void* stream, int* rc);
+bool wgrad_try(const dsgan_tc_wgrad_desc* d, const void* G, const void* X, float* dW, void* stream, int* rc);
 }  // namespace nm
 }  // namespace dsgan

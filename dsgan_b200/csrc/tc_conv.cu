@@ -731,6 +731,7 @@ int dsgan_tc_conv_wgrad(const dsgan_tc_wgrad_desc* d, const void* G, const void*
   DS_REQUIRE(((uintptr_t)G % 16 == 0) && ((uintptr_t)X % 16 == 0), "tc_conv_wgrad: unaligned");
   {
     int rc = 0;
+    if (nm::wgrad_try(d, G, X, dW, stream, &rc)) return rc;
     if (sc::wgrad_try(d, G, X, dW, stream, &rc)) return rc;
   }
   const int BN = d->Cx >= 128 ? 128 : 64;
