@@ -47,6 +47,12 @@ class TcWgradDesc(ctypes.Structure):
                 ("s_g", ctypes.c_longlong), ("s_x", ctypes.c_longlong)]
 
 
+class DwBranch(ctypes.Structure):
+    """Mirror of dsgan_dw_branch."""
+    _fields_ = [("w", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("dw", ctypes.c_void_p), ("db", ctypes.c_void_p),
+                ("k", ctypes.c_int), ("c0", ctypes.c_int), ("c", ctypes.c_int), ("pad_", ctypes.c_int)]
+
+
 _SCALARS = {"int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
             "unsigned long long": ctypes.c_ulonglong, "size_t": ctypes.c_size_t, "unsigned": ctypes.c_uint}
 

@@ -751,4 +751,37 @@ int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float
 #undef DWG_CASE
   return DS_LAUNCHED("dwconv_wgrad");
 }
+
+int dsgan_dwconv_multi_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int N, int H, int W,
+                           const dsgan_dw_branch* br, int nbr, int flip, int accumulate, void* stream) {
+  DS_REQUIRE(br && nbr >= 1 && nbr <= 4, "dwconv_multi_fwd: 1..4 branches");
+  const int es = dtype == DT_BF16 ? 2 : 4;
+  if (dtype == DT_BF16 && dw_mma_enabled()) {
+    int rc = 0;
+    if (dwm::multi_fwd_try((const bf16*)x, ld_x, (bf16*)y, ld_y, N, H, W, br, nbr, flip, accumulate, (cudaStream_t)stream, &rc))
+      return rc;
+  }
+  for (int i = 0; i < nbr; ++i) {   // shapes the one-launch kernel does not take: one call per branch
+    const int rc = dsgan_dwconv_fwd((const char*)x + (size_t)br[i].c0 * es, ld_x, br[i].w, br[i].bias,
+                                    (char*)y + (size_t)br[i].c0 * es, ld_y, dtype, N, H, W, br[i].c, br[i].k, flip, accumulate,
+                                    stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+int dsgan_dwconv_multi_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, int dtype, int N, int H, int W,
+                             const dsgan_dw_branch* br, int nbr, void* stream) {
+  DS_REQUIRE(br && nbr >= 1 && nbr <= 4, "dwconv_multi_wgrad: 1..4 branches");
+  const int es = dtype == DT_BF16 ? 2 : 4;
+  if (dtype == DT_BF16 && dw_mma_enabled()) {
+    int rc = 0;
+    if (dwm::multi_wgrad_try((const bf16*)x, ld_x, (const bf16*)dy, ld_dy, N, H, W, br, nbr, (cudaStream_t)stream, &rc)) return rc;
+  }
+  for (int i = 0; i < nbr; ++i) {
+    const int rc = dsgan_dwconv_wgrad((const char*)x + (size_t)br[i].c0 * es, ld_x, (const char*)dy + (size_t)br[i].c0 * es,
+                                      ld_dy, br[i].dw, br[i].db, dtype, N, H, W, br[i].c, br[i].k, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
 }

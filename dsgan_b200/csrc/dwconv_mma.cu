@@ -133,14 +133,12 @@ struct Geo {
 
 // forward / input gradient.  grid: (tile groups, channel blocks); a CTA walks tiles blockIdx.x, +gridDim.x, ...
 template <int K, int NT, int NS, bool SPLIT>
-__global__ void __launch_bounds__(256, 2) k_dw_mma(const bf16* __restrict__ x, int ldx, const float* __restrict__ w,
-                                                    const float* __restrict__ bias, bf16* __restrict__ y, int ldy, int N, int H,
-                                                    int W, int C, int flip, int acc_out, int tiles_x, int tiles_y,
-                                                    int total_tiles) {
+__device__ __forceinline__ void dw_mma_body(const bf16* __restrict__ x, int ldx, const float* __restrict__ w,
+                                            const float* __restrict__ bias, bf16* __restrict__ y, int ldy, int N, int H,
+                                            int W, int C, int flip, int acc_out, int tiles_x, int tiles_y,
+                                            int total_tiles, int c_base, unsigned char* dsm) {
   using G = Geo<K, NT, NS>;
-  extern __shared__ __align__(128) unsigned char dsm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int c_base = blockIdx.y * CB;
 
   // Toeplitz B fragments of this warp's two channels: b0 = T[2t, 2t+1][g], b1 = T[2t+8, 2t+9][g], T[k][n] = w[ky][k-n]
   uint32_t bh[2][K][2], bl[2][K][2];
@@ -260,15 +258,14 @@ __global__ void __launch_bounds__(256, 2) k_dw_mma(const bf16* __restrict__ x, i
 // weight (and bias) gradient.  Same tiling; the K fragments P_ky of a warp's two channels stay in registers across all tiles
 // of the CTA and are reduced once: diagonal kx of P_ky -> shared -> one atomicAdd per (channel, tap) per CTA.
 template <int K, int NT, int NS>
-__global__ void __launch_bounds__(256, 2) k_dw_mma_wgrad(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
-                                                          int lddy, float* __restrict__ dw, float* __restrict__ db, int N,
-                                                          int H, int W, int C, int tiles_x, int tiles_y, int total_tiles) {
+__device__ __forceinline__ void dw_mma_wgrad_body(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
+                                                  int lddy, float* __restrict__ dw, float* __restrict__ db, int N,
+                                                  int H, int W, int C, int tiles_x, int tiles_y, int total_tiles,
+                                                  int c_base, unsigned char* dsm) {
   using G = Geo<K, NT, NS>;
-  extern __shared__ __align__(128) unsigned char dsm[];
   unsigned char* sg = dsm + G::SMEM_X;
   float* sacc = reinterpret_cast<float*>(dsm + G::SMEM_X + G::SMEM_G);  // [16][K*K+1]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int c_base = blockIdx.y * CB;
   for (int i = tid; i < CB * (K * K + 1); i += 256) sacc[i] = 0.f;
   float acc[2][K][4], accb[2][4];
 #pragma unroll
@@ -346,6 +343,72 @@ __global__ void __launch_bounds__(256, 2) k_dw_mma_wgrad(const bf16* __restrict_
   }
 }
 
+
+template <int K, int NT, int NS, bool SPLIT>
+__global__ void __launch_bounds__(256, 2) k_dw_mma(const bf16* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, bf16* __restrict__ y, int ldy, int N, int H,
+                                                    int W, int C, int flip, int acc_out, int tiles_x, int tiles_y,
+                                                    int total_tiles) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  dw_mma_body<K, NT, NS, SPLIT>(x, ldx, w, bias, y, ldy, N, H, W, C, flip, acc_out, tiles_x, tiles_y, total_tiles,
+                                blockIdx.y * CB, dsm);
+}
+template <int K, int NT, int NS>
+__global__ void __launch_bounds__(256, 2) k_dw_mma_wgrad(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
+                                                          int lddy, float* __restrict__ dw, float* __restrict__ db, int N,
+                                                          int H, int W, int C, int tiles_x, int tiles_y, int total_tiles) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  dw_mma_wgrad_body<K, NT, NS>(x, ldx, dy, lddy, dw, db, N, H, W, C, tiles_x, tiles_y, total_tiles, blockIdx.y * CB, dsm);
+}
+
+// Several depthwise convolutions of different kernel sizes over disjoint channel slices of ONE tensor (MidMLKA.X3/X5/X7/X9,
+// MixConvNeXtML.py:94-97,110) in one launch: blockIdx.y walks the channel blocks of all branches.  The per-branch launches
+// were one tile per CTA and latency bound (~30 us each for 17 MB of traffic); four at once fill the machine.
+struct DwBranch {
+  const float* w; const float* bias; float* dw; float* db;
+  int k, c0, c, blk0;   // kernel size, channel slice [c0, c0+c), first channel block of the branch
+};
+struct DwMulti { DwBranch b[4]; int n; };
+
+template <int NT, int NS>
+__global__ void __launch_bounds__(256, 2) k_dw_mma_multi(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y, int ldy,
+                                                          int N, int H, int W, const DwMulti m, int flip, int acc_out,
+                                                          int tiles_x, int tiles_y, int total_tiles) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  int bi = 0;
+  while (bi + 1 < m.n && (int)blockIdx.y >= m.b[bi + 1].blk0) ++bi;
+  const DwBranch b = m.b[bi];
+  const int c_base = ((int)blockIdx.y - b.blk0) * CB;
+#define DWM_BODY(KK) dw_mma_body<KK, NT, NS, true>(x + b.c0, ldx, b.w, b.bias, y + b.c0, ldy, N, H, W, b.c, flip, acc_out, \
+                                                   tiles_x, tiles_y, total_tiles, c_base, dsm)
+  switch (b.k) {
+    case 3: DWM_BODY(3); break;
+    case 5: DWM_BODY(5); break;
+    case 7: DWM_BODY(7); break;
+    default: DWM_BODY(9); break;
+  }
+#undef DWM_BODY
+}
+template <int NT, int NS>
+__global__ void __launch_bounds__(256, 2) k_dw_mma_wgrad_multi(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ dy,
+                                                                int lddy, int N, int H, int W, const DwMulti m, int tiles_x,
+                                                                int tiles_y, int total_tiles) {
+  extern __shared__ __align__(128) unsigned char dsm[];
+  int bi = 0;
+  while (bi + 1 < m.n && (int)blockIdx.y >= m.b[bi + 1].blk0) ++bi;
+  const DwBranch b = m.b[bi];
+  const int c_base = ((int)blockIdx.y - b.blk0) * CB;
+#define DWM_BODY(KK) dw_mma_wgrad_body<KK, NT, NS>(x + b.c0, ldx, dy + b.c0, lddy, b.dw, b.db, N, H, W, b.c, tiles_x, tiles_y, \
+                                                   total_tiles, c_base, dsm)
+  switch (b.k) {
+    case 3: DWM_BODY(3); break;
+    case 5: DWM_BODY(5); break;
+    case 7: DWM_BODY(7); break;
+    default: DWM_BODY(9); break;
+  }
+#undef DWM_BODY
+}
+
 int sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -388,6 +451,47 @@ int launch_wgrad(const bf16* x, int ldx, const bf16* dy, int lddy, float* dw, fl
   return DS_LAUNCHED("dwconv_mma_wgrad");
 }
 
+
+template <int NT, int NS>
+int launch_multi_fwd(const bf16* x, int ldx, bf16* y, int ldy, int N, int H, int W, const DwMulti& m, int cblocks, int flip,
+                     int acc, cudaStream_t s) {
+  using G = Geo<9, NT, NS>;   // shared memory for the largest kernel size
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_dw_mma_multi<NT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_X); attr = true; }
+  const int tiles_x = cdiv(W, G::TX), tiles_y = cdiv(H, G::TY), total = N * tiles_x * tiles_y;
+  dim3 grid((unsigned)tile_groups(total, cblocks), (unsigned)cblocks);
+  k_dw_mma_multi<NT, NS><<<grid, 256, G::SMEM_X, s>>>(x, ldx, y, ldy, N, H, W, m, flip, acc, tiles_x, tiles_y, total);
+  return DS_LAUNCHED("dwconv_mma_multi");
+}
+template <int NT, int NS>
+int launch_multi_wgrad(const bf16* x, int ldx, const bf16* dy, int lddy, int N, int H, int W, const DwMulti& m, int cblocks,
+                       cudaStream_t s) {
+  using G = Geo<9, NT, NS>;
+  constexpr int smem = G::SMEM_X + G::SMEM_G + CB * (9 * 9 + 1) * 4;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(k_dw_mma_wgrad_multi<NT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  const int tiles_x = cdiv(W, G::TX), tiles_y = cdiv(H, G::TY), total = N * tiles_x * tiles_y;
+  dim3 grid((unsigned)tile_groups(total, cblocks), (unsigned)cblocks);
+  k_dw_mma_wgrad_multi<NT, NS><<<grid, 256, smem, s>>>(x, ldx, dy, lddy, N, H, W, m, tiles_x, tiles_y, total);
+  return DS_LAUNCHED("dwconv_mma_wgrad_multi");
+}
+
+// -> branch table; false if a branch is not eligible (kernel size, slice width / alignment)
+inline bool make_multi(const dsgan_dw_branch* br, int nbr, DwMulti* m, int* cblocks) {
+  if (nbr < 1 || nbr > 4) return false;
+  int blk = 0;
+  for (int i = 0; i < nbr; ++i) {
+    const dsgan_dw_branch& b = br[i];
+    if (!(b.k == 3 || b.k == 5 || b.k == 7 || b.k == 9) || b.c < 16 || b.c % 16 || b.c0 % 16) return false;
+    m->b[i].w = b.w; m->b[i].bias = b.bias; m->b[i].dw = b.dw; m->b[i].db = b.db;
+    m->b[i].k = b.k; m->b[i].c0 = b.c0; m->b[i].c = b.c; m->b[i].blk0 = blk;
+    blk += b.c / CB;
+  }
+  m->n = nbr;
+  *cblocks = blk;
+  return true;
+}
+
 inline bool shape_ok(const void* a, int lda, const void* b, int ldb, int H, int W, int C) {
   return C >= 16 && C % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) &&
          H >= 16 && W >= 32;
@@ -425,6 +529,26 @@ bool wgrad_try(const bf16* x, int ldx, const bf16* dy, int lddy, float* dw, floa
   }
 #undef DWM_WK
 #undef DWM_W
+}
+
+bool multi_fwd_try(const bf16* x, int ldx, bf16* y, int ldy, int N, int H, int W, const dsgan_dw_branch* br, int nbr, int flip,
+                   int accumulate, cudaStream_t s, int* rc) {
+  DwMulti m;
+  int cblocks = 0;
+  if (!make_multi(br, nbr, &m, &cblocks) || !shape_ok(x, ldx, y, ldy, H, W, 16)) return false;
+  if (W >= 64 && H >= 32) *rc = launch_multi_fwd<8, 2>(x, ldx, y, ldy, N, H, W, m, cblocks, flip, accumulate, s);
+  else if (H >= 32) *rc = launch_multi_fwd<4, 2>(x, ldx, y, ldy, N, H, W, m, cblocks, flip, accumulate, s);
+  else *rc = launch_multi_fwd<4, 1>(x, ldx, y, ldy, N, H, W, m, cblocks, flip, accumulate, s);
+  return true;
+}
+bool multi_wgrad_try(const bf16* x, int ldx, const bf16* dy, int lddy, int N, int H, int W, const dsgan_dw_branch* br, int nbr,
+                     cudaStream_t s, int* rc) {
+  DwMulti m;
+  int cblocks = 0;
+  if (!make_multi(br, nbr, &m, &cblocks) || !shape_ok(x, ldx, dy, lddy, H, W, 16)) return false;
+  if (H >= 32) *rc = launch_multi_wgrad<4, 2>(x, ldx, dy, lddy, N, H, W, m, cblocks, s);
+  else *rc = launch_multi_wgrad<4, 1>(x, ldx, dy, lddy, N, H, W, m, cblocks, s);
+  return true;
 }
 
 }  // namespace dwm

@@ -12,7 +12,7 @@ import ctypes
 
 import torch
 
-from ._lib import ConvDesc, PackJob, TcConvDesc, TcWgradDesc, lib, require_device
+from ._lib import ConvDesc, DwBranch, PackJob, TcConvDesc, TcWgradDesc, lib, require_device
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
@@ -89,7 +89,7 @@ class Param:
 
 FAMILY = {"fused_mlp_fwd": "dense", "fused_mlp_bwd": "dense", "mid_bias_grads": "ca", "conv_fwd": "dense", "conv_wgrad": "dense", "tc_gemm": "dense", "tc_wgrad": "dense", "tc_conv": "dense",
           "tc_conv_wgrad": "dense", "pack_conv_weight": "optim", "pack_conv_weights": "optim",
-          "colsum": "reduce", "dwconv_fwd": "dwconv", "dwconv_wgrad": "dwconv",
+          "colsum": "reduce", "dwconv_fwd": "dwconv", "dwconv_wgrad": "dwconv", "dwconv_multi_fwd": "dwconv", "dwconv_multi_wgrad": "dwconv",
           "inorm_stats": "norm", "inorm_apply": "norm", "inorm_bwd_stats": "norm", "inorm_bwd_apply": "norm",
           "maxpool_fwd": "pool", "maxpool_bwd": "pool", "multipool_fwd": "pool", "multipool_bwd": "pool", "ca_fwd": "ca", "ca_bwd": "ca", "scale_nc_fwd": "ca",
           "scale_nc_bwd_reduce": "ca", "scale_nc_bwd_apply": "ca",
@@ -674,6 +674,42 @@ def dwconv(ctx: Ctx, x: Var, w: Param, b: Param, k, out: Var = None, need_dx=Tru
         assert x.fused_act is None
         _label(ctx, x, "k%d dgrad" % k)
         L.dwconv_fwd(gi[0], gi[1], w.ptr, None, gp, gld, ctx.dt, x.N, x.H, x.W, x.C, k, 1, gacc, ctx.stream)
+    ctx.record(bwd)
+    return y
+
+
+def dwconv_multi(ctx: Ctx, x: Var, branches, out: Var = None, bias_grad=True):
+    """Depthwise convolutions of different kernel sizes on equal channel slices of x, one launch per pass
+    (MidMLKA.X3/X5/X7/X9, MixConvNeXtML.py:94-97,110).  branches: [(weight, bias, k), ...]; slice i = channels [i*q, (i+1)*q)."""
+    nb = len(branches)
+    q = x.C // nb
+    assert q * nb == x.C and nb <= 4
+    y = out if out is not None else ctx.new(x.N, x.H, x.W, x.C)
+    L = ctx.L
+
+    def table(with_grads, flip_bias):
+        arr = (DwBranch * nb)()
+        for i, (w, b, k) in enumerate(branches):
+            arr[i].w, arr[i].bias = w.ptr, (None if flip_bias else b.ptr)
+            arr[i].dw = w.gptr if with_grads else None
+            arr[i].db = b.gptr if (with_grads and bias_grad) else None
+            arr[i].k, arr[i].c0, arr[i].c = k, i * q, q
+        return arr
+    _label(ctx, x, "k" + "".join(str(k) for _, _, k in branches))
+    L.dwconv_multi_fwd(x.ptr, x.ld, y.ptr, y.ld, ctx.dt, x.N, x.H, x.W, table(False, False), nb, 0, 0, ctx.stream)
+    train_w = ctx.param_grads
+
+    def bwd():
+        gi = y.grad_in()
+        if gi is None:
+            return
+        if train_w:
+            _label(ctx, x, "multi")
+            L.dwconv_multi_wgrad(x.ptr, x.ld, gi[0], gi[1], ctx.dt, x.N, x.H, x.W, table(True, False), nb, ctx.stream)
+        gp, gld, gacc = x.grad_out()
+        assert x.fused_act is None
+        _label(ctx, x, "multi dgrad")
+        L.dwconv_multi_fwd(gi[0], gi[1], gp, gld, ctx.dt, x.N, x.H, x.W, table(False, True), nb, 1, gacc, ctx.stream)
     ctx.record(bwd)
     return y
 

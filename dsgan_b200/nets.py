@@ -13,8 +13,10 @@ import torch
 import torch.nn as nn
 
 from . import specs
+import os
+
 from .engine import (ACT_GELU, ACT_LEAKY, ACT_NONE, ACT_RELU, Ctx, Param, Var, add_n, block_mlp, ca_scale, concat_into,
-                     conv2d, conv_transpose2d, dwconv, fused_mlp_ok, image_to_nhwc, inorm, maxpool, multi_maxpool)
+                     conv2d, conv_transpose2d, dwconv, dwconv_multi, fused_mlp_ok, image_to_nhwc, inorm, maxpool, multi_maxpool)
 
 
 class ParamTree(nn.Module):
@@ -158,13 +160,17 @@ def _downskip(ctx: Ctx, P, name, x: Var, k, pooled: Var = None):
 
 def _midmlka(ctx: Ctx, P, p, x: Var):
     """MidMLKA (MixConvNeXtML.py:109-117)."""
-    q = x.C // 4
     cat = ctx.new(x.N, x.H, x.W, x.C)
     # The five biases of this module sit in front of an InstanceNorm (through the CA gate): their gradients are near-zero
     # sums that must not be taken over rounded bf16 tensors -> formed from fp32 plane statistics in ca_scale's backward.
-    for i, k in enumerate((3, 5, 7, 9)):
-        dwconv(ctx, x.slice(i * q, q), P["%s.X%d.weight" % (p, k)], P["%s.X%d.bias" % (p, k)], k,
-               out=cat.slice(i * q, q), bias_grad=False)
+    if os.environ.get("DSGAN_DW_MULTI", "1") != "0":
+        dwconv_multi(ctx, x, [(P["%s.X%d.weight" % (p, k)], P["%s.X%d.bias" % (p, k)], k) for k in (3, 5, 7, 9)], out=cat,
+                     bias_grad=False)
+    else:   # one launch per branch (A/B measurements)
+        q = x.C // 4
+        for i, k in enumerate((3, 5, 7, 9)):
+            dwconv(ctx, x.slice(i * q, q), P["%s.X%d.weight" % (p, k)], P["%s.X%d.bias" % (p, k)], k,
+                   out=cat.slice(i * q, q), bias_grad=False)
     o = conv2d(ctx, cat, P[p + ".conv.weight"], P[p + ".conv.bias"], 1, bias_grad=False)
     holder = {}
 

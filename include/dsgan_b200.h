@@ -199,6 +199,22 @@ int dsgan_dwconv_fwd(const void* x, int ld_x, const float* w, const float* bias,
 int dsgan_dwconv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, float* dw, float* db, int dtype,
                        int N, int H, int W, int C, int k, void* stream);
 
+/* Several depthwise convolutions with different kernel sizes over disjoint channel slices of ONE NHWC tensor in one launch
+ * (MidMLKA.X3/X5/X7/X9 on the four quarters of its input, MixConvNeXtML.py:94-97,110).  Branch i maps channels
+ * [c0, c0+c) of x to the same channels of y with its own fp32 weight [c,1,k,k] / bias [c] (bias may be NULL); semantics per
+ * branch as dsgan_dwconv_fwd / dsgan_dwconv_wgrad (dw +=, db += if not NULL).  nbr <= 4. */
+typedef struct {
+  const float* w;
+  const float* bias;
+  float* dw;
+  float* db;
+  int k, c0, c, pad_;
+} dsgan_dw_branch;
+int dsgan_dwconv_multi_fwd(const void* x, int ld_x, void* y, int ld_y, int dtype, int N, int H, int W,
+                           const dsgan_dw_branch* br, int nbr, int flip, int accumulate, void* stream);
+int dsgan_dwconv_multi_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, int dtype, int N, int H, int W,
+                             const dsgan_dw_branch* br, int nbr, void* stream);
+
 /* ---- InstanceNorm2d(affine=False, eps=1e-5) fused with activation / residual ---------------- */
 /* stats[n,c] = {shift, sum(x-shift), sum((x-shift)^2)} (fp32 [N,C,3], overwritten).  networks.py:25. */
 int dsgan_inorm_stats(const void* x, int ld_x, int dtype, int N, long long HW, int C, float* stats, void* stream);

@@ -176,6 +176,36 @@ def test_dwconv_mma(cfg, twice, monkeypatch):
 
 
 @pytest.mark.parametrize("prec", PREC)
+@pytest.mark.parametrize("shape", [(2, 128, 32, 64), (1, 64, 48, 40), (2, 32, 12, 10), (1, 256, 16, 16)])
+def test_dwconv_multi(prec, shape):
+    """MidMLKA's four depthwise branches (k = 3, 5, 7, 9 on the channel quarters) in one launch per pass"""
+    N, C, H, W = shape
+    q4 = C // 4
+    ctx = ctx_for(prec)
+    x = q(torch.randn(N, C, H, W, generator=_g(1)), prec)
+    dy = q(torch.randn(N, C, H, W, generator=_g(4)), prec)
+    ws = [torch.randn(q4, 1, k, k, generator=_g(10 + k)) / k for k in (3, 5, 7, 9)]
+    bs = [torch.randn(q4, generator=_g(20 + k)) * 0.1 for k in (3, 5, 7, 9)]
+    xr = x.clone().requires_grad_(True)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    br = [b.clone().requires_grad_(True) for b in bs]
+    yr = torch.cat([F.conv2d(xr[:, i * q4:(i + 1) * q4], wr[i], br[i], padding=k // 2, groups=q4)
+                    for i, k in enumerate((3, 5, 7, 9))], 1)
+    yr.backward(dy)
+    P = make_params(dict([("w%d" % i, w) for i, w in enumerate(ws)] + [("b%d" % i, b) for i, b in enumerate(bs)]))
+    xv = to_var(ctx, x)
+    yv = E.dwconv_multi(ctx, xv, [(P["w%d" % i], P["b%d" % i], k) for i, k in enumerate((3, 5, 7, 9))])
+    set_grad(ctx, yv, dy)
+    ctx.backward()
+    tol = TOL[prec]
+    assert rel(var_data(yv), yr.detach()) < tol
+    assert rel(var_grad(xv), xr.grad) < tol
+    for i in range(4):
+        assert rel(P["w%d" % i].grad.cpu(), wr[i].grad) < tol
+        assert rel(P["b%d" % i].grad.cpu(), br[i].grad) < tol
+
+
+@pytest.mark.parametrize("prec", PREC)
 @pytest.mark.parametrize("act", [None, "gelu", "leaky"])
 @pytest.mark.parametrize("with_res", [False, True])
 @pytest.mark.parametrize("shape", [(2, 3, 16, 16), (2, 64, 31, 31), (1, 130, 4, 4)])
