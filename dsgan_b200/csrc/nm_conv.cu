@@ -27,9 +27,9 @@ struct NmParams {
   int is_, oy0, ox0, ntaps;
   int dy[16], dx[16], slab[16];
   int dy_min, dx_min, rows, cols;   // staged input region of a tile
-  int tiles_x, tiles_y, total_tiles;
-  int act;
-  const bf16* in; const bf16* w; bf16* out; bf16* pre; const float* bias;
+  int tiles_x, tiles_y, total_tiles, nbuf;
+  int act, dact, accumulate, ld_aux;
+  const bf16* in; const bf16* w; bf16* out; bf16* pre; const float* bias; const bf16* aux;
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t a, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -51,13 +51,15 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// CP: padded channels per pixel in the staged tile (8 or 16); NTN: n8 tiles (Co padded to 8*NTN)
+// CP: channels per pixel in the staged tile (8 / 16: narrow inputs padded; 32 / 64: wide inputs of the narrow-OUTPUT layers);
+// NTN: n8 tiles (Co padded to 8*NTN)
 template <int CP, int NTN>
 __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
-  constexpr int CPB = CP * 2, CON = NTN * 8, SPITCH = CON * 2 + 16;
+  constexpr int CPB = CP >= 32 ? CP * 2 + 16 : CP * 2;   // pixel pitch: 8 consecutive pixels must hit 8 different 16-byte bank groups
+  constexpr int CON = NTN * 8, SPITCH = CON * 2 + 16, C8 = CP / 8, SPT = CP >= 16 ? CP / 16 : 1;
   extern __shared__ __align__(128) unsigned char dsm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nchunks = CP == 8 ? ((p.ntaps + 1) & ~1) : 2 * p.ntaps;   // 16-byte k chunks per weight row (even)
+  const int nchunks = CP == 8 ? ((p.ntaps + 1) & ~1) : C8 * p.ntaps;  // 16-byte k chunks per weight row (even)
   const int wpitch = ((nchunks & 1) ? nchunks : nchunks + 1) * 16;    // odd number of 16-byte units: conflict-free ldmatrix rows
   unsigned char* wsm = dsm;
   int* toff = reinterpret_cast<int*>(dsm + CON * wpitch);
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
   // weights -> shared [co][k chunk]; chunk = tap (CP 8) or (tap, channel half) (CP 16); zero beyond the taps
   for (int i = tid; i < CON * nchunks; i += THREADS) {
     const int n = i / nchunks, kc = i % nchunks;
-    const int tap = CP == 8 ? kc : kc >> 1, half = CP == 8 ? 0 : kc & 1;
+    const int tap = kc / C8, half = kc % C8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (tap < p.ntaps && n < p.co_pad)
       v = __ldg(reinterpret_cast<const uint4*>(p.w + ((size_t)p.slab[tap] * p.co_pad + n) * p.ci_pad + half * 8));
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
   // (register e of an ldmatrix.x4 holds channels 2t, 2t+1 of its 8-channel chunk), so the tile itself can be staged by
   // cp.async straight into shared memory, one tile ahead of the MMAs.
   auto cmask = [&](int c) { return (c < p.Ci ? 0x0000ffffu : 0u) | (c + 1 < p.Ci ? 0xffff0000u : 0u); };
-  const uint32_t amask_lo = cmask(2 * t), amask_hi = CP == 8 ? amask_lo : cmask(8 + 2 * t);
+  const uint32_t amask_lo = CP >= 32 ? 0xffffffffu : cmask(2 * t);   // (wide inputs: Ci == CP, nothing to clear)
+  const uint32_t amask_hi = CP >= 32 ? 0xffffffffu : (CP == 8 ? amask_lo : cmask(8 + 2 * t));
   const uint32_t wsm_u = (uint32_t)__cvta_generic_to_shared(wsm), tile_u = (uint32_t)__cvta_generic_to_shared(tile_s);
   const int px_l = (lane & 7) + ((lane >> 3) & 1) * 8, sel = lane >> 4;
   const int b_row = (lane & 7) + (lane >> 4) * 8, b_kc = (lane >> 3) & 1;
@@ -104,15 +107,23 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
     cp_async_commit();
   };
 
-  if ((int)blockIdx.x < p.total_tiles) prefetch(blockIdx.x, 0);
+  if ((int)blockIdx.x < p.total_tiles && p.nbuf == 2) prefetch(blockIdx.x, 0);
   int it = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
     const int img = tile / (p.tiles_x * p.tiles_y), ty = (tile / p.tiles_x) % p.tiles_y, tx = tile % p.tiles_x;
     const int gy0 = ty * TH, gx0 = tx * TW;
-    const int buf = it & 1;
-    cp_async_wait_all();
-    __syncthreads();   // this tile has landed for everyone; the other buffer (tile it-1) is consumed; weights visible
-    if (tile + (int)gridDim.x < p.total_tiles) prefetch(tile + gridDim.x, buf ^ 1);
+    int buf = 0;
+    if (p.nbuf == 2) {
+      buf = it & 1;
+      cp_async_wait_all();
+      __syncthreads();   // this tile has landed for everyone; the other buffer (tile it-1) is consumed; weights visible
+      if (tile + (int)gridDim.x < p.total_tiles) prefetch(tile + gridDim.x, buf ^ 1);
+    } else {             // (64-channel tiles: one buffer, so that two CTAs still fit an SM)
+      __syncthreads();
+      prefetch(tile, 0);
+      cp_async_wait_all();
+      __syncthreads();
+    }
 
     float acc[2][NTN][4];
 #pragma unroll
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
     for (int mt = 0; mt < 2; ++mt) abase[mt] = tile_u + buf * tile_bytes + ((warp * p.is_) * p.cols + (mt * 16 + px_l) * p.is_) * CPB;
 #pragma unroll 1
     for (int ks = 0; ks < ksteps; ++ks) {
-      const int off = CP == 8 ? toff[2 * ks + sel] : toff[ks] + sel * 16;
+      const int off = CP == 8 ? toff[2 * ks + sel] : toff[ks / SPT] + (ks % SPT) * 32 + sel * 16;
       uint32_t a[2][4];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
@@ -142,8 +153,34 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
         }
       }
     }
-    // epilogue: v = acc + bias ; pre = v ; out = act(v), through the warp's staging rows
+    // epilogue: v = acc + bias (+ out) ; v *= dact'(aux) ; pre = v ; out = act(v), through the warp's staging rows
     const int gy = gy0 + warp;
+    if (p.accumulate || p.dact) {   // input-gradient calls: old output / activation argument straight from global (4 bytes per lane)
+      const size_t rowb = ((size_t)img * p.Ho + gy + p.oy0) * p.Wo + p.ox0;
+#pragma unroll
+      for (int j = 0; j < NTN; ++j) {
+        const int ch = 8 * j + 2 * t;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int gx = gx0 + mt * 16 + g + 8 * h;
+            if (gy >= p.Hg || gx >= p.Wg || ch >= co8 * 8) continue;
+            float b0 = (p.bias && ch < p.Co) ? __ldg(p.bias + ch) : 0.f, b1 = (p.bias && ch + 1 < p.Co) ? __ldg(p.bias + ch + 1) : 0.f;
+            if (p.accumulate) {
+              const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(p.out + (rowb + gx) * p.ldc + ch);
+              b0 += __low2float(o); b1 += __high2float(o);
+            }
+            float v0 = acc[mt][j][2 * h] + b0, v1 = acc[mt][j][2 * h + 1] + b1;
+            if (p.dact) {
+              const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(p.aux + (rowb + gx) * p.ld_aux + ch);
+              v0 *= act_bwd_fast(p.dact, __low2float(a)); v1 *= act_bwd_fast(p.dact, __high2float(a));
+            }
+            acc[mt][j][2 * h] = v0 - ((p.bias && ch < p.Co) ? __ldg(p.bias + ch) : 0.f);       // the passes below add the bias back
+            acc[mt][j][2 * h + 1] = v1 - ((p.bias && ch + 1 < p.Co) ? __ldg(p.bias + ch + 1) : 0.f);
+          }
+      }
+    }
 #pragma unroll 1
     for (int pass = p.pre ? 0 : 1; pass < 2; ++pass) {
       __syncwarp();
@@ -364,18 +401,21 @@ bool conv_try(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, 
     const char* e = getenv("DSGAN_NM_CONV");
     if (e && e[0] == '0') return false;
   }
-  if (!(d->Ci == 1 || d->Ci == 3 || d->Ci == 6 || d->Ci == 12) || d->Co > 64 || d->Co < 8) return false;
-  if (d->nclass != 1 || d->out_stride != 1 || d->accumulate || d->dact || aux) return false;
+  const bool narrow_in = (d->Ci == 1 || d->Ci == 3 || d->Ci == 6 || d->Ci == 12) && d->Co <= 64 && d->Co >= 8;
+  const bool narrow_out = !narrow_in && d->Co <= 16 && (d->Ci == 16 || d->Ci == 32 || d->Ci == 64);
+  if (!narrow_in && !narrow_out) return false;
+  if (d->nclass != 1 || d->out_stride != 1) return false;
   if (d->ntaps[0] < 1 || d->ntaps[0] > 16 || (d->in_stride != 1 && d->in_stride != 2)) return false;
-  const int CP = d->Ci <= 8 ? 8 : 16;
+  const int CP = narrow_in ? (d->Ci <= 8 ? 8 : 16) : d->Ci;
   const int co8 = (d->Co + 7) / 8 * 8;
   if (d->ld_in % 8 || d->ld_in < (d->Ci + 7) / 8 * 8 || (uintptr_t)in % 16 || (uintptr_t)w_slabs % 16 || d->ci_pad % 8) return false;
   auto out_ok = [&](const void* ptr, int ld) {
     if (!ptr) return true;
     return (uintptr_t)ptr % 16 == 0 && ld % 8 == 0 && ld >= co8;
   };
-  if (!out_ok(out, d->ld_out) || !out_ok(pre_out, d->ld_pre)) return false;
-  if (d->Co % 8 && (d->ld_out != co8 || (pre_out && d->ld_pre != co8))) return false;   // ragged Co: whole-pitch tensors only
+  if (!out_ok(out, d->ld_out) || !out_ok(pre_out, d->ld_pre) || !out_ok(aux, d->ld_aux)) return false;
+  if (d->dact && !aux) return false;
+  if (d->Co % 8 && (d->ld_out != co8 || (pre_out && d->ld_pre != co8) || (aux && d->ld_aux != co8))) return false;   // ragged Co: whole-pitch tensors only
   NmParams p;
   memset(&p, 0, sizeof(p));
   p.N = d->N; p.Hg = d->Hg; p.Wg = d->Wg; p.Hi = d->Hi; p.Wi = d->Wi; p.Ho = d->Ho; p.Wo = d->Wo;
@@ -395,17 +435,23 @@ bool conv_try(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, 
   const long long total = (long long)d->N * p.tiles_x * p.tiles_y;
   if (total >= (1LL << 31)) return false;
   p.total_tiles = (int)total;
-  p.act = d->act;
+  p.act = d->act; p.dact = aux ? d->dact : 0; p.accumulate = d->accumulate; p.ld_aux = d->ld_aux;
   p.in = (const bf16*)in; p.w = (const bf16*)w_slabs; p.out = (bf16*)out; p.pre = (bf16*)pre_out; p.bias = bias;
+  p.aux = (const bf16*)aux;
   const int NTN = co8 <= 16 ? 2 : (co8 <= 32 ? 4 : 8);
   const int CON = NTN * 8;
-  const int nchunks = CP == 8 ? ((p.ntaps + 1) & ~1) : 2 * p.ntaps;
+  const int nchunks = CP == 8 ? ((p.ntaps + 1) & ~1) : (CP / 8) * p.ntaps;
   const int wpitch = ((nchunks & 1) ? nchunks : nchunks + 1) * 16;
-  const size_t smem = (size_t)CON * wpitch + 64 + (size_t)8 * 32 * (CON * 2 + 16) + 2 * (size_t)((p.rows * p.cols * CP * 2 + 127) & ~127);
+  const int ppb = CP >= 32 ? CP * 2 + 16 : CP * 2;
+  const size_t tile_bytes = (size_t)((p.rows * p.cols * ppb + 127) & ~127);
+  const size_t fixed = (size_t)CON * wpitch + 64 + (size_t)8 * 32 * (CON * 2 + 16);
+  p.nbuf = fixed + 2 * tile_bytes <= 100 * 1024 ? 2 : 1;
+  const size_t smem = fixed + p.nbuf * tile_bytes;
   if (smem > 100 * 1024) return false;
   cudaStream_t s = (cudaStream_t)stream;
 #define NM_CASE(CPV, NT) if (CP == CPV && NTN == NT) { *rc = launch<CPV, NT>(p, smem, s); return true; }
-  NM_CASE(8, 2) NM_CASE(8, 4) NM_CASE(8, 8) NM_CASE(16, 2) NM_CASE(16, 4) NM_CASE(16, 8)
+  if (getenv("DSGAN_NM_TRACE")) fprintf(stderr, "nm_conv: Ci=%d Co=%d taps=%d CP=%d NTN=%d nbuf=%d smem=%zu\n", d->Ci, d->Co, p.ntaps, CP, NTN, p.nbuf, smem);
+  NM_CASE(8, 2) NM_CASE(8, 4) NM_CASE(8, 8) NM_CASE(16, 2) NM_CASE(16, 4) NM_CASE(16, 8) NM_CASE(32, 2) NM_CASE(64, 2)
 #undef NM_CASE
   return false;
 }

@@ -14,6 +14,7 @@
 // 4-stage smem ring, double-buffered TMEM accumulator).
 #include "tc_common.cuh"
 #include "../../include/dsgan_b200.h"
+#include <stdlib.h>
 #include "sc_conv.cuh"
 #include "nm_conv.cuh"
 #include <map>
@@ -680,6 +681,11 @@ int dsgan_tc_conv(const dsgan_tc_conv_desc* d, const void* in, const void* w_sla
               d->nclass == 1 && d->in_stride == 1 && d->out_stride == 1 && d->ntaps[0] == 9 && d->oy0[0] == 0 &&
               d->ox0[0] == 0;
   for (int t = 0; halo && t < d->ntaps[0]; ++t) halo = d->dy[t] >= -1 && d->dy[t] <= 1 && d->dx[t] >= -1 && d->dx[t] <= 1;
+  if (halo && d->Co <= 16) {   // 64 -> 3: an N = 8 mma.sync tile wastes less than the BN = 32 tcgen05 tile (nm_conv.cu)
+    const char* e = getenv("DSGAN_NM_NOUT");
+    int rc = 0;
+    if (!(e && e[0] == '0') && nm::conv_try(d, in, w_slabs, bias, out, pre_out, aux, stream, &rc)) return rc;
+  }
   if (halo) {
     CUtensorMap ta, tb;
     if (map_input_halo(&ta, in, d->N, d->Hi, d->Wi, d->Ci, d->ld_in)) return 1;
