@@ -19,3 +19,4 @@ python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra --no-graph > $
 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 900 --csv --log-file $O/final_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra --no-graph > $O/final_ncu.log 2>&1
 tail -1 $O/final_ncu.log
+python -c "import __graft_entry__ as g; g.smoke()" > $O/final_smoke.txt 2>&1; tail -1 $O/final_smoke.txt
