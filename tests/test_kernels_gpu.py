@@ -208,7 +208,8 @@ def test_dwconv_multi(prec, shape):
 @pytest.mark.parametrize("prec", PREC)
 @pytest.mark.parametrize("act", [None, "gelu", "leaky"])
 @pytest.mark.parametrize("with_res", [False, True])
-@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (2, 64, 31, 31), (1, 130, 4, 4)])
+@pytest.mark.parametrize("shape", [(2, 3, 16, 16), (2, 64, 31, 31), (1, 130, 4, 4), (2, 128, 32, 32), (1, 16, 64, 64),
+                                   (3, 256, 16, 16), (1, 64, 72, 72)])
 def test_instance_norm(prec, act, with_res, shape):
     ctx = ctx_for(prec)
     x = q(torch.randn(shape, generator=_g(1)) * 2 + 3, prec)   # non-zero mean: exercises the shifted sums
