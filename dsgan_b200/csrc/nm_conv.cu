@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
   const int wpitch = ((nchunks & 1) ? nchunks : nchunks + 1) * 16;    // odd number of 16-byte units: conflict-free ldmatrix rows
   unsigned char* wsm = dsm;
   int* toff = reinterpret_cast<int*>(dsm + CON * wpitch);
-  unsigned char* stage = reinterpret_cast<unsigned char*>(toff + 16);
+  float* sbias = reinterpret_cast<float*>(toff + 16);                  // [CON] (0 beyond Co / without bias)
+  unsigned char* stage = reinterpret_cast<unsigned char*>(sbias + CON);
   unsigned char* tile_s = stage + 8 * 32 * SPITCH;                    // two buffers of tile_bytes
   const int tile_bytes = (p.rows * p.cols * CPB + 127) & ~127;
 
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
       v = __ldg(reinterpret_cast<const uint4*>(p.w + ((size_t)p.slab[tap] * p.co_pad + n) * p.ci_pad + half * 8));
     *reinterpret_cast<uint4*>(wsm + n * wpitch + kc * 16) = v;
   }
+  if (tid >= 32 && tid < 32 + CON) sbias[tid - 32] = (p.bias && tid - 32 < p.Co) ? __ldg(p.bias + tid - 32) : 0.f;
   if (tid < 16) {
     const int tp = tid < p.ntaps ? tid : p.ntaps - 1;   // a dummy tap (zero weights) must still point inside the tile
     toff[tid] = ((p.dy[tp] - p.dy_min) * p.cols + (p.dx[tp] - p.dx_min)) * CPB;
@@ -97,12 +99,17 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
     const int img = tile / (p.tiles_x * p.tiles_y), ty = (tile / p.tiles_x) % p.tiles_y, tx = tile % p.tiles_x;
     const int iy0 = ty * TH * p.is_ + p.dy_min, ix0 = tx * TW * p.is_ + p.dx_min;
     const uint32_t dst = tile_u + buf * tile_bytes;
-    for (int i = tid; i < p.rows * p.cols * (CP / 8); i += THREADS) {
-      const int h = i % (CP / 8), pxl = (i / (CP / 8)) % p.cols, pyl = i / ((CP / 8) * p.cols);
-      const int iy = iy0 + pyl, ix = ix0 + pxl;
-      const bool ok = iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi && h * 8 < p.ld_in;
-      const bf16* src = ok ? p.in + (((size_t)img * p.Hi + iy) * p.Wi + ix) * p.ld_in + h * 8 : p.in;
-      cp_async16_zfill(dst + (pyl * p.cols + pxl) * CPB + h * 16, src, ok);
+    const int rowchunks = p.cols * C8;   // 16-byte chunks per staged row; a warp walks one row (no runtime divisions)
+    for (int pyl = warp; pyl < p.rows; pyl += THREADS / 32) {
+      const int iy = iy0 + pyl;
+      const bool rok = iy >= 0 && iy < p.Hi;
+      const bf16* rsrc = p.in + (((size_t)img * p.Hi + (rok ? iy : 0)) * p.Wi) * p.ld_in;
+      const uint32_t rdst = dst + pyl * p.cols * CPB;
+      for (int c = lane; c < rowchunks; c += 32) {
+        const int h = c % C8, pxl = c / C8, ix = ix0 + pxl;
+        const bool ok = rok && ix >= 0 && ix < p.Wi && h * 8 < p.ld_in;
+        cp_async16_zfill(rdst + pxl * CPB + h * 16, ok ? rsrc + (size_t)ix * p.ld_in + h * 8 : p.in, ok);
+      }
     }
     cp_async_commit();
   };
@@ -155,66 +162,80 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_conv(const NmParams p) {
     }
     // epilogue: v = acc + bias (+ out) ; v *= dact'(aux) ; pre = v ; out = act(v), through the warp's staging rows
     const int gy = gy0 + warp;
-    if (p.accumulate || p.dact) {   // input-gradient calls: old output / activation argument straight from global (4 bytes per lane)
-      const size_t rowb = ((size_t)img * p.Ho + gy + p.oy0) * p.Wo + p.ox0;
-#pragma unroll
-      for (int j = 0; j < NTN; ++j) {
-        const int ch = 8 * j + 2 * t;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int gx = gx0 + mt * 16 + g + 8 * h;
-            if (gy >= p.Hg || gx >= p.Wg || ch >= co8 * 8) continue;
-            float b0 = (p.bias && ch < p.Co) ? __ldg(p.bias + ch) : 0.f, b1 = (p.bias && ch + 1 < p.Co) ? __ldg(p.bias + ch + 1) : 0.f;
-            if (p.accumulate) {
-              const __nv_bfloat162 o = *reinterpret_cast<const __nv_bfloat162*>(p.out + (rowb + gx) * p.ldc + ch);
-              b0 += __low2float(o); b1 += __high2float(o);
-            }
-            float v0 = acc[mt][j][2 * h] + b0, v1 = acc[mt][j][2 * h + 1] + b1;
-            if (p.dact) {
-              const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(p.aux + (rowb + gx) * p.ld_aux + ch);
-              v0 *= act_bwd_fast(p.dact, __low2float(a)); v1 *= act_bwd_fast(p.dact, __high2float(a));
-            }
-            acc[mt][j][2 * h] = v0 - ((p.bias && ch < p.Co) ? __ldg(p.bias + ch) : 0.f);       // the passes below add the bias back
-            acc[mt][j][2 * h + 1] = v1 - ((p.bias && ch + 1 < p.Co) ? __ldg(p.bias + ch + 1) : 0.f);
-          }
-      }
-    }
+    // Input-gradient calls (accumulate / dact): the sums are staged un-activated and the rest of the contract is applied on the
+    // 16-byte vectors of the store loop (old output and aux read coalesced).  pass 0 = pre-activation copy, 1 = activated output,
+    // 2 = staged raw for the input-gradient form.
+    const bool igrad = p.accumulate || p.dact;
 #pragma unroll 1
-    for (int pass = p.pre ? 0 : 1; pass < 2; ++pass) {
+    for (int pass = igrad ? 2 : (p.pre ? 0 : 1); pass < 3; ++pass) {
+      if (pass == 2 && !igrad) break;
       __syncwarp();
 #pragma unroll
-      for (int j = 0; j < NTN; ++j) {
-        const int ch = 8 * j + 2 * t;
-        const float b0 = (p.bias && ch < p.Co) ? __ldg(p.bias + ch) : 0.f, b1 = (p.bias && ch + 1 < p.Co) ? __ldg(p.bias + ch + 1) : 0.f;
+      for (int mt = 0; mt < 2; ++mt) {
+        float v[NTN * 4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          float v[4] = {acc[mt][j][0] + b0, acc[mt][j][1] + b1, acc[mt][j][2] + b0, acc[mt][j][3] + b1};
-          if (pass == 1) {
+        for (int j = 0; j < NTN; ++j) {
+          const float2 bb = *reinterpret_cast<const float2*>(sbias + 8 * j + 2 * t);
+          v[j * 4 + 0] = acc[mt][j][0] + bb.x; v[j * 4 + 1] = acc[mt][j][1] + bb.y;
+          v[j * 4 + 2] = acc[mt][j][2] + bb.x; v[j * 4 + 3] = acc[mt][j][3] + bb.y;
+        }
+        if (pass == 1) act_fwd_fast_vec<NTN * 4>(p.act, v);   // one uniform test of `act`, then a straight loop
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = act_fwd_fast(p.act, v[e]);
-          }
-          *reinterpret_cast<uint32_t*>(my_stage + (mt * 16 + g) * SPITCH + ch * 2) = pack_bf2(v[0], v[1]);
-          *reinterpret_cast<uint32_t*>(my_stage + (mt * 16 + g + 8) * SPITCH + ch * 2) = pack_bf2(v[2], v[3]);
+        for (int j = 0; j < NTN; ++j) {
+          const int ch = 8 * j + 2 * t;
+          *reinterpret_cast<uint32_t*>(my_stage + (mt * 16 + g) * SPITCH + ch * 2) = pack_bf2(v[j * 4], v[j * 4 + 1]);
+          *reinterpret_cast<uint32_t*>(my_stage + (mt * 16 + g + 8) * SPITCH + ch * 2) = pack_bf2(v[j * 4 + 2], v[j * 4 + 3]);
         }
       }
       __syncwarp();
-      bf16* dst = pass == 0 ? p.pre : p.out;
-      const int ld = pass == 0 ? p.ld_pre : p.ldc;
       if (gy < p.Hg) {
         const size_t rowbase = ((size_t)img * p.Ho + gy + p.oy0) * p.Wo + p.ox0;
-        for (int i = lane; i < 32 * NTN; i += 32) {
-          const int px = i / NTN, c16 = i % NTN, gx = gx0 + px;
-          if (gx < p.Wg && c16 < co8)
-            *reinterpret_cast<uint4*>(dst + (rowbase + gx) * ld + c16 * 8) =
-                *reinterpret_cast<const uint4*>(my_stage + px * SPITCH + c16 * 16);
+        if (pass < 2) {
+          bf16* dst = pass == 0 ? p.pre : p.out;
+          const int ld = pass == 0 ? p.ld_pre : p.ldc;
+          for (int i = lane; i < 32 * NTN; i += 32) {
+            const int px = i / NTN, c16 = i % NTN, gx = gx0 + px;
+            if (gx < p.Wg && c16 < co8)
+              *reinterpret_cast<uint4*>(dst + (rowbase + gx) * ld + c16 * 8) =
+                  *reinterpret_cast<const uint4*>(my_stage + px * SPITCH + c16 * 16);
+          }
+        } else {
+#pragma unroll 1
+          for (int i = lane; i < 32 * NTN; i += 32) {
+            const int px = i / NTN, c16 = i % NTN, gx = gx0 + px;
+            if (gx >= p.Wg || c16 >= co8) continue;
+            const uint4 sv = *reinterpret_cast<const uint4*>(my_stage + px * SPITCH + c16 * 16);
+            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { f[2 * e] = __uint_as_float(sw[e] << 16); f[2 * e + 1] = __uint_as_float(sw[e] & 0xffff0000u); }
+            bf16* op = p.out + (rowbase + gx) * p.ldc + c16 * 8;
+            if (p.accumulate) {
+              const uint4 ov = *reinterpret_cast<const uint4*>(op);
+              const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { f[2 * e] += __uint_as_float(ow[e] << 16); f[2 * e + 1] += __uint_as_float(ow[e] & 0xffff0000u); }
+            }
+            if (p.dact) {
+              const uint4 av = *reinterpret_cast<const uint4*>(p.aux + (rowbase + gx) * p.ld_aux + c16 * 8);
+              const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+              float a[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { a[2 * e] = __uint_as_float(aw[e] << 16); a[2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u); }
+              act_bwd_fast_mul<8>(p.dact, f, a);
+            }
+            if (p.pre)
+              *reinterpret_cast<uint4*>(p.pre + (rowbase + gx) * p.ld_pre + c16 * 8) =
+                  make_uint4(pack_bf2(f[0], f[1]), pack_bf2(f[2], f[3]), pack_bf2(f[4], f[5]), pack_bf2(f[6], f[7]));
+            act_fwd_fast_vec<8>(p.act, f);
+            *reinterpret_cast<uint4*>(op) = make_uint4(pack_bf2(f[0], f[1]), pack_bf2(f[2], f[3]), pack_bf2(f[4], f[5]), pack_bf2(f[6], f[7]));
+          }
         }
       }
+      if (pass == 2) break;
     }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // Weight gradient of the narrow layers:  dW[tap][m][n] += sum_px G[px][m] * X[px*xs + tap][n]  with one side of 1/3/6/12
@@ -444,7 +465,7 @@ bool conv_try(const dsgan_tc_conv_desc* d, const void* in, const void* w_slabs, 
   const int wpitch = ((nchunks & 1) ? nchunks : nchunks + 1) * 16;
   const int ppb = CP >= 32 ? CP * 2 + 16 : CP * 2;
   const size_t tile_bytes = (size_t)((p.rows * p.cols * ppb + 127) & ~127);
-  const size_t fixed = (size_t)CON * wpitch + 64 + (size_t)8 * 32 * (CON * 2 + 16);
+  const size_t fixed = (size_t)CON * wpitch + 64 + (size_t)CON * 4 + (size_t)8 * 32 * (CON * 2 + 16);
   p.nbuf = fixed + 2 * tile_bytes <= 100 * 1024 ? 2 : 1;
   const size_t smem = fixed + p.nbuf * tile_bytes;
   if (smem > 100 * 1024) return false;

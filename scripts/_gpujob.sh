@@ -1,5 +1,5 @@
-timeout 900 python -m pytest tests/test_kernels_gpu.py -q -k "instance_norm" > gpurun_out/r2_t20.txt 2>&1; tail -4 gpurun_out/r2_t20.txt
-timeout 900 python -m pytest tests/test_step_gpu.py -q -x > gpurun_out/r2_t18.txt 2>&1; tail -2 gpurun_out/r2_t18.txt
-for v in 0 1 0 1; do
-DSGAN_IN_FUSED=$v python bench.py --no-cpu-baseline --no-extra --steps 10 > gpurun_out/r2_bench14.json 2> gpurun_out/r2_bench14.err; echo "fused=$v $(cut -c75-175 gpurun_out/r2_bench14.json)"
+timeout 900 python -m pytest tests/test_kernels_gpu.py -q -k "conv" > gpurun_out/r2_t17.txt 2>&1; tail -2 gpurun_out/r2_t17.txt
+python scripts/bench_kernels.py --only smallch --out gpurun_out/r2_k_sc3.jsonl 2>&1 | grep " fwd\"" | cut -c1-100
+for v in 1 1; do
+python bench.py --no-cpu-baseline --no-extra --steps 10 > gpurun_out/r2_bench15.json 2> gpurun_out/r2_bench15.err; echo "$(cut -c75-175 gpurun_out/r2_bench15.json)"
 done
