@@ -12,8 +12,9 @@
 // channel-planar bf16 tile in shared memory through ldmatrix, whose per-lane row addresses make the ky row shift free (the
 // reason this is mma.sync + ldmatrix and not tcgen05: a UMMA shared-memory descriptor cannot start at an arbitrary row of a
 // swizzled tile, and the shift would have to be paid as 7 shifted copies of the tile or 7 cross-lane TMEM reductions).
-// Weights are applied as w = hi + lo (two bf16 MMAs on the same data fragment), so the products carry 16 mantissa bits of the
-// fp32 weight -- results match the fp32-weight CUDA-core kernel to fp32 accumulation order.
+// Weights enter as bf16 like those of every other tensor-core layer of the bf16 mode (fp32 accumulate); DSGAN_DW_SPLIT=1 applies
+// them as hi + lo (two MMAs on the same data fragment, 16 mantissa bits).  The step-level parity numbers are the same either
+// way (fake_B 2.07e-2, G gradients 1.2e-2 at 16x256x256) and the split costs 14 % of the forward kernel, so it is off.
 //
 // The weight gradient uses the transposed product: for 16 rows of dy and 8 columns, P_ky[m, n] = sum_y in[y+ky, x0+m] *
 // dy[y, x0+n] accumulated over ALL tiles into one 16x8 fragment per ky; dw[ky, kx] is the sum of its kx-th diagonal.
@@ -23,12 +24,16 @@
 // 8 consecutive rows hit 8 different 16-byte bank groups), results are written back in place into the dead rows of the planes
 // and leave as 16-byte NHWC vectors.  Algorithmic traffic: read x once, write y once (wgrad: read x and dy once).
 #include "dwconv_mma.cuh"
+#include <stdlib.h>
 
 namespace dsgan {
 namespace dwm {
 namespace {
 
 constexpr int CB = 16;  // channels per CTA
+#ifndef DW_STAGE_U
+#define DW_STAGE_U 3   // pixel pairs per thread in flight while staging (6 independent 32-byte loads; 4 measured the same)
+#endif
 
 __device__ __forceinline__ void ldsm_x4(uint32_t a, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
@@ -90,7 +95,7 @@ template <int ROWS, int COLS, int PITCHB>
 __device__ __forceinline__ void stage_planar(unsigned char* sm, const bf16* __restrict__ src, int ld, int n, int H, int W,
                                              int yorg, int xorg, int c_base, int C, int tid, bool wide) {
   static_assert(COLS % 2 == 0, "pixel pairs");
-  constexpr int PAIRS = COLS / 2, ITEMS = ROWS * PAIRS, PLANE = ROWS * PITCHB, U = 2;
+  constexpr int PAIRS = COLS / 2, ITEMS = ROWS * PAIRS, PLANE = ROWS * PITCHB, U = DW_STAGE_U;
   const bool two = c_base + 8 < C;
   for (int i0 = tid; i0 < ITEMS; i0 += 256 * U) {
     uint32_t v[U][2][8];
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(256, 2) k_dw_mma_multi(const bf16* __restrict_
   while (bi + 1 < m.n && (int)blockIdx.y >= m.b[bi + 1].blk0) ++bi;
   const DwBranch b = m.b[bi];
   const int c_base = ((int)blockIdx.y - b.blk0) * CB;
-#define DWM_BODY(KK) dw_mma_body<KK, NT, NS, true>(x + b.c0, ldx, b.w, b.bias, y + b.c0, ldy, N, H, W, b.c, flip, acc_out, \
+#define DWM_BODY(KK) dw_mma_body<KK, NT, NS, false>(x + b.c0, ldx, b.w, b.bias, y + b.c0, ldy, N, H, W, b.c, flip, acc_out, \
                                                    tiles_x, tiles_y, total_tiles, c_base, dsm)
   switch (b.k) {
     case 3: DWM_BODY(3); break;
@@ -432,10 +437,17 @@ int launch_fwd(const bf16* x, int ldx, const float* w, const float* bias, bf16* 
                int flip, int acc, cudaStream_t s) {
   using G = Geo<K, NT, NS>;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(k_dw_mma<K, NT, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_X); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(k_dw_mma<K, NT, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_X);
+    cudaFuncSetAttribute(k_dw_mma<K, NT, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_X);
+    attr = true;
+  }
   const int tiles_x = cdiv(W, G::TX), tiles_y = cdiv(H, G::TY), total = N * tiles_x * tiles_y, cblocks = cdiv(C, CB);
   dim3 grid((unsigned)tile_groups(total, cblocks), (unsigned)cblocks);
-  k_dw_mma<K, NT, NS, true><<<grid, 256, G::SMEM_X, s>>>(x, ldx, w, bias, y, ldy, N, H, W, C, flip, acc, tiles_x, tiles_y, total);
+  static int split = -1;   // DSGAN_DW_SPLIT=1: weights as bf16 hi + lo (two MMAs per fragment, 16 mantissa bits); default: one bf16 MMA
+  if (split < 0) { const char* e = getenv("DSGAN_DW_SPLIT"); split = (e && e[0] == '1') ? 1 : 0; }
+  if (split) k_dw_mma<K, NT, NS, true><<<grid, 256, G::SMEM_X, s>>>(x, ldx, w, bias, y, ldy, N, H, W, C, flip, acc, tiles_x, tiles_y, total);
+  else k_dw_mma<K, NT, NS, false><<<grid, 256, G::SMEM_X, s>>>(x, ldx, w, bias, y, ldy, N, H, W, C, flip, acc, tiles_x, tiles_y, total);
   return DS_LAUNCHED("dwconv_mma");
 }
 template <int K, int NT, int NS>

@@ -170,8 +170,8 @@ def test_dwconv_mma(cfg, twice, monkeypatch):
     tol = TOL["bf16"]
     assert rel(y1, yr.detach()) < tol and rel(dx1, xr.grad) < tol
     assert rel(dw1, wr.grad) < 1e-3 and rel(db1, br.grad) < 1e-3     # exact bf16 products, fp32 sums
-    # same arithmetic as the fp32-weight CUDA-core kernels up to the summation order (hi + lo weight split)
-    assert rel(y1, y0) < 2e-3 and rel(dx1, dx0) < 3e-3
+    # against the fp32-weight CUDA-core kernels: the tensor-core path rounds the taps to bf16 (2^-9 relative per tap)
+    assert rel(y1, y0) < 5e-3 and rel(dx1, dx0) < 5e-3
     assert rel(dw1, dw0) < 1e-4 and rel(db1, db0) < 1e-4
 
 
