@@ -278,21 +278,31 @@ __global__ void __launch_bounds__(THREADS, 2) k_nm_wgrad(const NmWgParams p) {
   auto prefetch = [&](int tile, int buf) {
     const int img = tile / (p.tiles_x * p.tiles_y), ty = (tile / p.tiles_x) % p.tiles_y, tx = tile % p.tiles_x;
     const int gy0 = ty * TH, gx0 = tx * TW;
-    const int cg8 = p.cgp / 8, cx8 = p.cxp / 8;
-    for (int i = tid; i < TH * TW * cg8; i += THREADS) {
-      const int h = i % cg8, px = (i / cg8) % TW, py = i / (cg8 * TW);
-      const int gy = gy0 + py, gx = gx0 + px;
-      const bool ok = gy < p.Hg && gx < p.Wg && h * 8 < p.ld_g;
-      const bf16* src = ok ? p.G + (((size_t)img * p.Hg + gy) * p.Wg + gx) * p.ld_g + h * 8 : p.G;
-      cp_async16_zfill(g_u + buf * p.gbytes + (py * TW + px) * p.gpitch + h * 16, src, ok);
+    const int cg8 = p.cgp / 8, cx8 = p.cxp / 8;   // powers of two (1..8)
+    const int gsh = __ffs(cg8) - 1, xsh = __ffs(cx8) - 1;
+    // a warp walks one staged row, a lane its 16-byte chunks: no divisions by run-time extents in the copy loops
+    for (int py = warp; py < TH; py += THREADS / 32) {
+      const int gy = gy0 + py;
+      const bool rok = gy < p.Hg;
+      const bf16* rsrc = p.G + (((size_t)img * p.Hg + (rok ? gy : 0)) * p.Wg) * p.ld_g;
+      const uint32_t rdst = g_u + buf * p.gbytes + py * TW * p.gpitch;
+      for (int c = lane; c < TW * cg8; c += 32) {
+        const int px = c >> gsh, h = c & (cg8 - 1), gx = gx0 + px;
+        const bool ok = rok && gx < p.Wg && h * 8 < p.ld_g;
+        cp_async16_zfill(rdst + px * p.gpitch + h * 16, ok ? rsrc + (size_t)gx * p.ld_g + h * 8 : p.G, ok);
+      }
     }
     const int iy0 = gy0 * p.xs + p.dy_min, ix0 = gx0 * p.xs + p.dx_min;
-    for (int i = tid; i < p.xrows * p.xcols * cx8; i += THREADS) {
-      const int h = i % cx8, pxl = (i / cx8) % p.xcols, pyl = i / (cx8 * p.xcols);
-      const int iy = iy0 + pyl, ix = ix0 + pxl;
-      const bool ok = iy >= 0 && iy < p.Hx && ix >= 0 && ix < p.Wx && h * 8 < p.ld_x;
-      const bf16* src = ok ? p.X + (((size_t)img * p.Hx + iy) * p.Wx + ix) * p.ld_x + h * 8 : p.X;
-      cp_async16_zfill(x_u + buf * p.xbytes + (pyl * p.xcols + pxl) * p.xpitch + h * 16, src, ok);
+    for (int pyl = warp; pyl < p.xrows; pyl += THREADS / 32) {
+      const int iy = iy0 + pyl;
+      const bool rok = iy >= 0 && iy < p.Hx;
+      const bf16* rsrc = p.X + (((size_t)img * p.Hx + (rok ? iy : 0)) * p.Wx) * p.ld_x;
+      const uint32_t rdst = x_u + buf * p.xbytes + pyl * p.xcols * p.xpitch;
+      for (int c = lane; c < p.xcols * cx8; c += 32) {
+        const int pxl = c >> xsh, h = c & (cx8 - 1), ix = ix0 + pxl;
+        const bool ok = rok && ix >= 0 && ix < p.Wx && h * 8 < p.ld_x;
+        cp_async16_zfill(rdst + pxl * p.xpitch + h * 16, ok ? rsrc + (size_t)ix * p.ld_x + h * 8 : p.X, ok);
+      }
     }
     cp_async_commit();
   };
