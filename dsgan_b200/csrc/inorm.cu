@@ -234,9 +234,13 @@ __device__ __forceinline__ void norm_consts(const float* stats, int n, int C, in
   }
 }
 
+// ACT >= 0: the activation is a compile-time constant (GELU / LeakyReLU / none: every norm of the step), so the other
+// activations' code and the per-pair tests of `act` drop out of the loops; ACT < 0: run-time `act_rt`.
+template <int ACT>
 __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x, int ldx, const float* __restrict__ stats,
                                                       const bf16* __restrict__ res, int ldr, bf16* __restrict__ y, int ldy,
-                                                      long long HW, int C, int act, int VCHUNK) {
+                                                      long long HW, int C, int act_rt, int VCHUNK) {
+  const int act = ACT >= 0 ? ACT : act_rt;
   const VLanes l = vlanes(C);
   if (l.tp >= l.pl) return;
   const int n = blockIdx.y;
@@ -264,10 +268,12 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
   }
 }
 
+template <int ACT>
 __global__ void __launch_bounds__(256, 4) k_in_bwd_stats_v8(const bf16* __restrict__ x, int ldx,
                                                           const float* __restrict__ stats, const bf16* __restrict__ res,
                                                           int ldr, const bf16* __restrict__ dy, int lddy, long long HW,
-                                                          int C, int act, float* __restrict__ bst, int VCHUNK) {
+                                                          int C, int act_rt, float* __restrict__ bst, int VCHUNK) {
+  const int act = ACT >= 0 ? ACT : act_rt;
   __shared__ float sacc[2][256];
   const VLanes l = vlanes(C);
   const int n = blockIdx.y;
@@ -319,14 +325,15 @@ __global__ void __launch_bounds__(256, 4) k_in_bwd_stats_v8(const bf16* __restri
 // SUMS: additionally accumulate the per-(n, c) sum of the fp32 dx values BEFORE they are rounded to bf16 (and before any
 // fan-in add).  A bias that feeds an InstanceNorm has the gradient sum_p dx[p] = 0 in exact arithmetic; summing the rounded bf16
 // tensor afterwards (the old colsum pass) turned that structural zero into rounding noise of the size of a real gradient.
-template <bool SUMS>
+template <bool SUMS, int ACT>
 __global__ void __launch_bounds__(256, 3) k_in_bwd_apply_v8(const bf16* __restrict__ x, int ldx,
                                                           const float* __restrict__ stats, const bf16* __restrict__ res,
                                                           int ldr, const bf16* __restrict__ dy, int lddy,
                                                           const float* __restrict__ bst, bf16* __restrict__ dx, int lddx,
                                                           int acc_dx, bf16* __restrict__ dres, int lddr, int acc_dres,
-                                                          long long HW, int C, int act, int VCHUNK,
+                                                          long long HW, int C, int act_rt, int VCHUNK,
                                                           float* __restrict__ dbias, float* __restrict__ dsum_nc) {
+  const int act = ACT >= 0 ? ACT : act_rt;
   __shared__ float sacc[SUMS ? 256 : 1];
   const VLanes l = vlanes(C);
   if (SUMS) {
@@ -457,9 +464,12 @@ int dsgan_inorm_apply(const void* x, int ld_x, const float* stats, const void* r
   if (dtype == DT_BF16 && v8ok(C, {x, res, y}, {ld_x, res ? ld_res : 0, ld_y})) {
     int ch;
     static int slots = 0;
-    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_apply_v8, &slots));
-    k_in_apply_v8<<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (bf16*)y,
-                                                        ld_y, HW, C, act, ch);
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_apply_v8<ACT_GELU>, &slots));
+#define IN_APPLY(A) k_in_apply_v8<A><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, \
+                                                                          (bf16*)y, ld_y, HW, C, act, ch)
+    if (act == ACT_GELU) IN_APPLY(ACT_GELU); else if (act == ACT_LEAKY) IN_APPLY(ACT_LEAKY); else if (act == ACT_NONE) IN_APPLY(ACT_NONE);
+    else IN_APPLY(-1);
+#undef IN_APPLY
     return DS_LAUNCHED("inorm_apply_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
@@ -474,9 +484,12 @@ int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const voi
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy}, {ld_x, res ? ld_res : 0, ld_dy})) {
     int ch;
     static int slots = 0;
-    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_stats_v8, &slots));
-    k_in_bwd_stats_v8<<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, (const bf16*)dy, ld_dy, HW,
-                                          C, act, bstats, ch);
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_stats_v8<ACT_GELU>, &slots));
+#define IN_BSTATS(A) k_in_bwd_stats_v8<A><<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,       \
+                                                              (const bf16*)dy, ld_dy, HW, C, act, bstats, ch)
+    if (act == ACT_GELU) IN_BSTATS(ACT_GELU); else if (act == ACT_LEAKY) IN_BSTATS(ACT_LEAKY); else if (act == ACT_NONE) IN_BSTATS(ACT_NONE);
+    else IN_BSTATS(-1);
+#undef IN_BSTATS
     return DS_LAUNCHED("inorm_bwd_stats_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
@@ -490,21 +503,24 @@ int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const voi
                           void* stream) {
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy, dx, dres}, {ld_x, res ? ld_res : 0, ld_dy, ld_dx, dres ? ld_dres : 0})) {
     int ch;
+#define IN_BAPPLY(SUMS, A, DB, DS)                                                                                              \
+  k_in_bwd_apply_v8<SUMS, A><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,       \
+                                                                   (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,    \
+                                                                   (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch, DB, DS)
+#define IN_BAPPLY_ACT(SUMS, DB, DS)                                                                                             \
+  if (act == ACT_GELU) IN_BAPPLY(SUMS, ACT_GELU, DB, DS); else if (act == ACT_LEAKY) IN_BAPPLY(SUMS, ACT_LEAKY, DB, DS);         \
+  else if (act == ACT_NONE) IN_BAPPLY(SUMS, ACT_NONE, DB, DS); else IN_BAPPLY(SUMS, -1, DB, DS)
     if (dbias || dsum_nc) {
       static int slots = 0;
-      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<true>, &slots));
-      k_in_bwd_apply_v8<true><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
-                                                                    (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
-                                                                    (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch, dbias,
-                                                                    dsum_nc);
+      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<true, ACT_GELU>, &slots));
+      IN_BAPPLY_ACT(true, dbias, dsum_nc);
     } else {
       static int slots = 0;
-      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<false>, &slots));
-      k_in_bwd_apply_v8<false><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,
-                                                                     (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,
-                                                                     (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch, nullptr,
-                                                                     nullptr);
+      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<false, ACT_GELU>, &slots));
+      IN_BAPPLY_ACT(false, nullptr, nullptr);
     }
+#undef IN_BAPPLY_ACT
+#undef IN_BAPPLY
     return DS_LAUNCHED("inorm_bwd_apply_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
