@@ -236,11 +236,13 @@ __device__ __forceinline__ void norm_consts(const float* stats, int n, int C, in
 
 // ACT >= 0: the activation is a compile-time constant (GELU / LeakyReLU / none: every norm of the step), so the other
 // activations' code and the per-pair tests of `act` drop out of the loops; ACT < 0: run-time `act_rt`.
-template <int ACT>
+// PLAIN: no residual / no second output / no accumulation -- the common case, with those paths compiled out.
+template <int ACT, bool PLAIN>
 __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x, int ldx, const float* __restrict__ stats,
-                                                      const bf16* __restrict__ res, int ldr, bf16* __restrict__ y, int ldy,
+                                                      const bf16* __restrict__ res_rt, int ldr, bf16* __restrict__ y, int ldy,
                                                       long long HW, int C, int act_rt, int VCHUNK) {
   const int act = ACT >= 0 ? ACT : act_rt;
+  const bf16* __restrict__ res = PLAIN ? nullptr : res_rt;
   const VLanes l = vlanes(C);
   if (l.tp >= l.pl) return;
   const int n = blockIdx.y;
@@ -268,12 +270,13 @@ __global__ void __launch_bounds__(256) k_in_apply_v8(const bf16* __restrict__ x,
   }
 }
 
-template <int ACT>
+template <int ACT, bool PLAIN>
 __global__ void __launch_bounds__(256, 4) k_in_bwd_stats_v8(const bf16* __restrict__ x, int ldx,
-                                                          const float* __restrict__ stats, const bf16* __restrict__ res,
+                                                          const float* __restrict__ stats, const bf16* __restrict__ res_rt,
                                                           int ldr, const bf16* __restrict__ dy, int lddy, long long HW,
                                                           int C, int act_rt, float* __restrict__ bst, int VCHUNK) {
   const int act = ACT >= 0 ? ACT : act_rt;
+  const bf16* __restrict__ res = PLAIN ? nullptr : res_rt;
   __shared__ float sacc[2][256];
   const VLanes l = vlanes(C);
   const int n = blockIdx.y;
@@ -325,15 +328,18 @@ __global__ void __launch_bounds__(256, 4) k_in_bwd_stats_v8(const bf16* __restri
 // SUMS: additionally accumulate the per-(n, c) sum of the fp32 dx values BEFORE they are rounded to bf16 (and before any
 // fan-in add).  A bias that feeds an InstanceNorm has the gradient sum_p dx[p] = 0 in exact arithmetic; summing the rounded bf16
 // tensor afterwards (the old colsum pass) turned that structural zero into rounding noise of the size of a real gradient.
-template <bool SUMS, int ACT>
+template <bool SUMS, int ACT, bool PLAIN>
 __global__ void __launch_bounds__(256, 3) k_in_bwd_apply_v8(const bf16* __restrict__ x, int ldx,
-                                                          const float* __restrict__ stats, const bf16* __restrict__ res,
+                                                          const float* __restrict__ stats, const bf16* __restrict__ res_rt,
                                                           int ldr, const bf16* __restrict__ dy, int lddy,
                                                           const float* __restrict__ bst, bf16* __restrict__ dx, int lddx,
-                                                          int acc_dx, bf16* __restrict__ dres, int lddr, int acc_dres,
+                                                          int acc_dx_rt, bf16* __restrict__ dres_rt, int lddr, int acc_dres,
                                                           long long HW, int C, int act_rt, int VCHUNK,
                                                           float* __restrict__ dbias, float* __restrict__ dsum_nc) {
   const int act = ACT >= 0 ? ACT : act_rt;
+  const bf16* __restrict__ res = PLAIN ? nullptr : res_rt;
+  bf16* __restrict__ dres = PLAIN ? nullptr : dres_rt;
+  const int acc_dx = PLAIN ? 0 : acc_dx_rt;
   __shared__ float sacc[SUMS ? 256 : 1];
   const VLanes l = vlanes(C);
   if (SUMS) {
@@ -464,9 +470,14 @@ int dsgan_inorm_apply(const void* x, int ld_x, const float* stats, const void* r
   if (dtype == DT_BF16 && v8ok(C, {x, res, y}, {ld_x, res ? ld_res : 0, ld_y})) {
     int ch;
     static int slots = 0;
-    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_apply_v8<ACT_GELU>, &slots));
-#define IN_APPLY(A) k_in_apply_v8<A><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res, \
-                                                                          (bf16*)y, ld_y, HW, C, act, ch)
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_apply_v8<ACT_GELU, false>, &slots));
+#define IN_APPLY(A)                                                                                                         \
+  do {                                                                                                                      \
+    if (res) k_in_apply_v8<A, false><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res,   \
+                                                                           ld_res, (bf16*)y, ld_y, HW, C, act, ch);       \
+    else k_in_apply_v8<A, true><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, nullptr, 0, (bf16*)y,    \
+                                                                      ld_y, HW, C, act, ch);                                \
+  } while (0)
     if (act == ACT_GELU) IN_APPLY(ACT_GELU); else if (act == ACT_LEAKY) IN_APPLY(ACT_LEAKY); else if (act == ACT_NONE) IN_APPLY(ACT_NONE);
     else IN_APPLY(-1);
 #undef IN_APPLY
@@ -484,9 +495,14 @@ int dsgan_inorm_bwd_stats(const void* x, int ld_x, const float* stats, const voi
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy}, {ld_x, res ? ld_res : 0, ld_dy})) {
     int ch;
     static int slots = 0;
-    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_stats_v8<ACT_GELU>, &slots));
-#define IN_BSTATS(A) k_in_bwd_stats_v8<A><<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,       \
-                                                              (const bf16*)dy, ld_dy, HW, C, act, bstats, ch)
+    dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_stats_v8<ACT_GELU, false>, &slots));
+#define IN_BSTATS(A)                                                                                                        \
+  do {                                                                                                                      \
+    if (res) k_in_bwd_stats_v8<A, false><<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,          \
+                                                            (const bf16*)dy, ld_dy, HW, C, act, bstats, ch);               \
+    else k_in_bwd_stats_v8<A, true><<<g8, 256, 0, s>>>((const bf16*)x, ld_x, stats, nullptr, 0, (const bf16*)dy, ld_dy, HW, \
+                                                       C, act, bstats, ch);                                                 \
+  } while (0)
     if (act == ACT_GELU) IN_BSTATS(ACT_GELU); else if (act == ACT_LEAKY) IN_BSTATS(ACT_LEAKY); else if (act == ACT_NONE) IN_BSTATS(ACT_NONE);
     else IN_BSTATS(-1);
 #undef IN_BSTATS
@@ -503,24 +519,28 @@ int dsgan_inorm_bwd_apply(const void* x, int ld_x, const float* stats, const voi
                           void* stream) {
   if (dtype == DT_BF16 && v8ok(C, {x, res, dy, dx, dres}, {ld_x, res ? ld_res : 0, ld_dy, ld_dx, dres ? ld_dres : 0})) {
     int ch;
+    const bool plain = !res && !dres && !acc_dx;
+#define IN_BAPPLY_P(SUMS, A, P, DB, DS)                                                                                         \
+  k_in_bwd_apply_v8<SUMS, A, P><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,    \
+                                                                      (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx, \
+                                                                      (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch, DB, DS)
 #define IN_BAPPLY(SUMS, A, DB, DS)                                                                                              \
-  k_in_bwd_apply_v8<SUMS, A><<<g8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld_x, stats, (const bf16*)res, ld_res,       \
-                                                                   (const bf16*)dy, ld_dy, bstats, (bf16*)dx, ld_dx, acc_dx,    \
-                                                                   (bf16*)dres, ld_dres, acc_dres, HW, C, act, ch, DB, DS)
+  do { if (plain) IN_BAPPLY_P(SUMS, A, true, DB, DS); else IN_BAPPLY_P(SUMS, A, false, DB, DS); } while (0)
 #define IN_BAPPLY_ACT(SUMS, DB, DS)                                                                                             \
   if (act == ACT_GELU) IN_BAPPLY(SUMS, ACT_GELU, DB, DS); else if (act == ACT_LEAKY) IN_BAPPLY(SUMS, ACT_LEAKY, DB, DS);         \
   else if (act == ACT_NONE) IN_BAPPLY(SUMS, ACT_NONE, DB, DS); else IN_BAPPLY(SUMS, -1, DB, DS)
     if (dbias || dsum_nc) {
       static int slots = 0;
-      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<true, ACT_GELU>, &slots));
+      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<true, ACT_GELU, false>, &slots));
       IN_BAPPLY_ACT(true, dbias, dsum_nc);
     } else {
       static int slots = 0;
-      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<false, ACT_GELU>, &slots));
+      dim3 g8 = v8grid(HW, N, C, &ch, resident_blocks(k_in_bwd_apply_v8<false, ACT_GELU, false>, &slots));
       IN_BAPPLY_ACT(false, nullptr, nullptr);
     }
 #undef IN_BAPPLY_ACT
 #undef IN_BAPPLY
+#undef IN_BAPPLY_P
     return DS_LAUNCHED("inorm_bwd_apply_v8");
   }
   dim3 grid(cdiv(HW, CHUNK), N);
