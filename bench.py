@@ -261,8 +261,9 @@ def run_ours(args):
 
     # ---- end-to-end arm: host batch in, losses out, every step -------------------------------------
     def e2e_step():
-        model.set_input(batch)
+        model.set_input(batch)             # (takes the copy prefetch_input() started during the previous step, if any)
         model.optimize_parameters()
+        model.prefetch_input(batch)        # next batch: pinned host -> device on the copy stream, under this step's kernels
         model.get_current_losses()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)

@@ -51,6 +51,7 @@ class Pix2PixModel(BaseModel):
         self.ctxV = networks.get_ctx(self.device, prec["vgg"])
         self.world = parallel.world_size()
         self._in_buf, self._gs = {}, None
+        self._stage = None     # prefetch_input(): staging buffers + events of the next batch
         self.use_graph = bool(int(getattr(opt, "cuda_graph", 1))) and self.isTrain
         if self.isTrain:
             use_sigmoid = opt.no_lsgan
@@ -91,11 +92,53 @@ class Pix2PixModel(BaseModel):
         buf.copy_(src, non_blocking=True)
         return buf
 
+    def prefetch_input(self, input):
+        """Optional: start the host-to-device copy of the NEXT batch on a copy stream while the current step is still running
+        (what a DataLoader with pinned memory + non_blocking copies gives the reference).  A following set_input() of the same
+        tensors only waits for that copy and moves it device-to-device into the persistent input buffers."""
+        if not self.isTrain:
+            return
+        AtoB = self.opt.which_direction == "AtoB"
+        a, b = input["A" if AtoB else "B"], input["B" if AtoB else "A"]
+        st = self._stage
+        if st is None or st["A"].shape != a.shape or st["B"].shape != b.shape:
+            st = self._stage = {"A": torch.empty(a.shape, dtype=torch.float32, device=self.device),
+                                "B": torch.empty(b.shape, dtype=torch.float32, device=self.device),
+                                "stream": torch.cuda.Stream(self.device), "ready": torch.cuda.Event(),
+                                "consumed": None, "key": None}
+        cs = st["stream"]
+        if st["consumed"] is not None:
+            cs.wait_event(st["consumed"])          # the previous staged batch has been moved out of the staging buffers
+        with torch.cuda.stream(cs):
+            st["A"].copy_(a, non_blocking=True)
+            st["B"].copy_(b, non_blocking=True)
+            st["ready"].record(cs)
+        st["key"] = (a.data_ptr(), b.data_ptr(), tuple(a.shape))
+
+    def _take_staged(self, a, b):
+        st = self._stage
+        if st is None or st["key"] != (a.data_ptr(), b.data_ptr(), tuple(a.shape)):
+            return False
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(st["ready"])
+        for name in ("A", "B"):
+            buf = self._in_buf.get(name)
+            if buf is None or buf.shape != st[name].shape:
+                buf = self._in_buf[name] = torch.empty(st[name].shape, dtype=torch.float32, device=self.device)
+            buf.copy_(st[name], non_blocking=True)
+        if st["consumed"] is None:
+            st["consumed"] = torch.cuda.Event()
+        st["consumed"].record(cur)
+        st["key"] = None
+        self.real_A, self.real_B = self._in_buf["A"], self._in_buf["B"]
+        return True
+
     def set_input(self, input):
         AtoB = self.opt.which_direction == "AtoB"
         a, b = input["A" if AtoB else "B"], input["B" if AtoB else "A"]
         if self.isTrain:
-            self.real_A, self.real_B = self._to_input_buffer("A", a), self._to_input_buffer("B", b)
+            if not self._take_staged(a, b):
+                self.real_A, self.real_B = self._to_input_buffer("A", a), self._to_input_buffer("B", b)
         else:
             self.real_A = a.to(self.device, non_blocking=True).float().contiguous()
             self.real_B = b.to(self.device, non_blocking=True).float().contiguous()

@@ -189,3 +189,31 @@ def test_batch_metrics_reuse_the_step_outputs():
     assert abs(float(met["ssim"]) - want_ssim) < 1e-4
     mse = float((((fake.clamp(-1, 1) + 1) * 127.5 - (real + 1) * 127.5) ** 2).mean())
     assert abs(float(met["psnr"]) - 10 * math.log10(255 ** 2 / mse)) < 1e-3
+
+
+def test_prefetch_input_is_equivalent_to_set_input():
+    """prefetch_input() stages the next batch on a copy stream; set_input() of the same tensors takes the staged copy, any other
+    batch falls back to the direct copy.  The loss trajectory (CUDA-graph mode) equals the one without prefetching."""
+    PG, PD, PV = O.init_params_G(20), O.init_params_D(20), O.init_params_vgg(20)
+    batches = [O.synthetic_pair(2, 64, 64, seed=60 + i) for i in range(5)]
+    pinned = [{"A": A.pin_memory(), "B": B.pin_memory(), "A_paths": [""], "B_paths": [""]} for A, B in batches]
+    traj = {}
+    for prefetch in (False, True):
+        m, _ = _model(["--precision", "fp32", "--cuda_graph", "1"])
+        m.netG.load_state_dict(PG)
+        m.netD.load_state_dict(PD)
+        m.vgg.load_state_dict(PV, strict=False)
+        rows = []
+        for i, data in enumerate(pinned):
+            m.set_input(data)
+            assert torch.equal(m.real_A.cpu(), data["A"]) and torch.equal(m.real_B.cpu(), data["B"])
+            m.optimize_parameters()
+            if prefetch and i + 1 < len(pinned):
+                # stage the wrong batch first on odd steps: set_input must then ignore it and copy directly
+                m.prefetch_input(pinned[i + 1] if i % 2 == 0 else pinned[0])
+            torch.cuda.synchronize()
+            rows.append([float(m._loss[j]) for j in range(7)])
+        traj[prefetch] = rows
+    for a, b in zip(traj[False], traj[True]):
+        for u, v in zip(a, b):
+            assert abs(u - v) <= 2e-3 * max(1.0, abs(u)), (a, b)
