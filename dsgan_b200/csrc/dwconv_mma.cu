@@ -471,7 +471,9 @@ int launch_multi_fwd(const bf16* x, int ldx, bf16* y, int ldy, int N, int H, int
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_dw_mma_multi<NT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_X); attr = true; }
   const int tiles_x = cdiv(W, G::TX), tiles_y = cdiv(H, G::TY), total = N * tiles_x * tiles_y;
-  dim3 grid((unsigned)tile_groups(total, cblocks), (unsigned)cblocks);
+  // Branches differ 3x in cost (k = 3 .. 9): tile groups are sized as for ONE branch, so that the grid is several waves of short
+  // CTAs and the block scheduler balances the branches (a one-wave persistent grid finished with the k = 9 CTAs alone).
+  dim3 grid((unsigned)tile_groups(total, (cblocks + m.n - 1) / m.n), (unsigned)cblocks);
   k_dw_mma_multi<NT, NS><<<grid, 256, G::SMEM_X, s>>>(x, ldx, y, ldy, N, H, W, m, flip, acc, tiles_x, tiles_y, total);
   return DS_LAUNCHED("dwconv_mma_multi");
 }
@@ -483,7 +485,7 @@ int launch_multi_wgrad(const bf16* x, int ldx, const bf16* dy, int lddy, int N, 
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(k_dw_mma_wgrad_multi<NT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
   const int tiles_x = cdiv(W, G::TX), tiles_y = cdiv(H, G::TY), total = N * tiles_x * tiles_y;
-  dim3 grid((unsigned)tile_groups(total, cblocks), (unsigned)cblocks);
+  dim3 grid((unsigned)tile_groups(total, (cblocks + m.n - 1) / m.n), (unsigned)cblocks);
   k_dw_mma_wgrad_multi<NT, NS><<<grid, 256, smem, s>>>(x, ldx, dy, lddy, N, H, W, m, tiles_x, tiles_y, total);
   return DS_LAUNCHED("dwconv_mma_wgrad_multi");
 }
